@@ -1,0 +1,153 @@
+/*
+ * rqb200 -- C ABI of the B200-native RQ-VAE / RQ-Transformer sampling engine (sm_100a).
+ *
+ * The reference (kakaobrain/rq-vae-transformer @ 341395e) is pure Python/PyTorch and has no plugin / FFI
+ * registry; its boundary for this path is the Python class surface of `rqvae.models`.  Each
+ * entry point below replaces the *library calls* behind one reference method and is what a ctypes binding in
+ * the reference's own classes would call (INTEGRATION.md shows those stubs).  Conventions:
+ *   - plain pointers and sizes only; every `const T*` / `T*` tensor argument is a DEVICE pointer unless the
+ *     name ends in `_host`; row-major, contiguous; `stream` is a cudaStream_t passed as void*.
+ *   - return 0 on success, a negative RQB200_E* code otherwise; `rqb200_last_error()` gives the message.
+ *   - entry points never allocate device memory and never synchronise the device; scratch space is a caller
+ *     supplied workspace whose size is reported by the matching `*_workspace_bytes` query.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns RQB200_ENODEV.
+ */
+#ifndef RQB200_H
+#define RQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RQB200_OK 0
+#define RQB200_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define RQB200_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define RQB200_ENODEV (-3)   /* no CUDA device                               */
+#define RQB200_EWORKSPACE (-4) /* workspace too small                        */
+#define RQB200_ESTATE (-5)   /* engine not finalised / tensor missing        */
+
+#define RQB200_F32 0
+#define RQB200_BF16 1
+#define RQB200_F16 2
+
+/* arithmetic modes (DESIGN.md "two modes") */
+#define RQB200_MODE_EXACT 0  /* fp32 weights + fp32 FFMA: the bit-exact-indices gate                    */
+#define RQB200_MODE_FAST 1   /* bf16 (AR) / fp16 (conv) operands on tcgen05, fp32 accumulate: throughput */
+
+const char* rqb200_last_error(void);
+int rqb200_version(void);
+int rqb200_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------ P1
+ * RQBottleneck.quantize  (rqvae/models/rqvae/quantizations.py:237-271; VQEmbedding.compute_distances :43-62,
+ * find_nearest_embedding :64-69, embed :144-146).  x [N,C] f32, codebook [K,C] f32 (weight[:-1], no padding row).
+ * codes [N,D] int64.  quant_list (nullable) [D,N,C] f32 = the D cumulative aggregates (quant_list[i] of the
+ * reference).  residual_out (nullable) [N,C] f32 = x - quant_list[D-1].  C must be 256 (quantizations.py:181). */
+int rqb200_rq_quantize(const float* x, const float* codebook, int64_t N, int K, int C, int D, int64_t* codes,
+                       float* quant_list, float* residual_out, void* stream);
+
+/* RQBottleneck.embed_code (quantizations.py:297-311): out[n,:] = sum_d codebook[codes[n,d],:]  (order d=0..D-1). */
+int rqb200_rq_embed_sum(const int64_t* codes, const float* codebook, int64_t N, int D, int K, int C, float* out,
+                        void* stream);
+/* RQBottleneck.embed_code_with_depth (quantizations.py:313-334): out[n,d,:] = codebook[codes[n,d],:]. */
+int rqb200_rq_embed_depth(const int64_t* codes, const float* codebook, int64_t N, int D, int K, int C, float* out,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------ sampler
+ * sample_from_logits (rqvae/utils/utils.py:82-123; top_k_logits :60-64, top_p_probs :67-79).  logits [B,V] f32.
+ * q (nullable) [B,V] f32 Exp(1) noise: torch.multinomial(probs,1) == argmax(probs/q) (SURVEY.md finding 7);
+ * NULL means q == 1 (arg-max of the filtered distribution).  top_k <= 0 or >= V disables top-k; top_p >= 1
+ * takes the reference's p = 1.0 branch.  out_idx [B] int64.  V <= 16384.  No host sync (the reference's NaN
+ * check syncs; here NaN -> -inf is done on the device). */
+int rqb200_sample_logits(const float* logits, const float* q, int B, int V, float temperature, int top_k,
+                         float top_p, int64_t* out_idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ P3
+ * RQTransformer (rqvae/models/rqtransformer/transformers.py) -- cached AR sampling. */
+typedef struct rqb200_block_weights {
+    const void *wqkv, *wproj, *w1, *w2;            /* [3E,E] (rows: query|key|value), [E,E], [4E,E], [E,4E]; weight dtype */
+    const float *bqkv, *bproj, *b1, *b2;           /* f32 biases */
+    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;    /* f32 */
+} rqb200_block_weights;
+
+typedef struct rqb200_ar_config {
+    int32_t embed_dim, n_head, n_body, n_head_layers;  /* E, heads (E/heads must be 64), body / head depth   */
+    int32_t vocab, H, W, D;                             /* V and block_size                                    */
+    int32_t vocab_cond, cond_len;                       /* cond_emb rows, block_size_cond (>=1)                */
+    int32_t code_dim, codebook_size;                    /* C (=256) and K of the RQ-VAE codebook               */
+    int32_t mode;                                       /* RQB200_MODE_*                                       */
+    int32_t weight_dtype;                               /* RQB200_F32 (exact) or RQB200_BF16 (fast)            */
+} rqb200_ar_config;
+
+typedef struct rqb200_ar_weights {
+    const float *pos_emb_cond, *pos_emb_hw, *pos_emb_d;  /* [cond_len,E], [H*W,E], [D,E] f32                    */
+    const float* cond_emb;                                /* [vocab_cond,E] f32                                  */
+    const void *w_in, *w_head, *w_cls;                    /* [E,C], [E,C], [V,E]; weight dtype                   */
+    const float *b_in, *b_head, *b_cls;
+    const float *cls_ln_w, *cls_ln_b;
+    const float* codebook;                                /* [K,C] f32 (model_aux.get_code_emb_with_depth)       */
+    const rqb200_block_weights* body;                     /* host array [n_body]                                 */
+    const rqb200_block_weights* head;                     /* host array [n_head_layers]                          */
+} rqb200_ar_weights;
+
+typedef struct rqb200_ar rqb200_ar;
+
+rqb200_ar* rqb200_ar_create(const rqb200_ar_config* cfg, const rqb200_ar_weights* w);
+void rqb200_ar_destroy(rqb200_ar* h);
+size_t rqb200_ar_workspace_bytes(const rqb200_ar* h, int B);
+
+/* RQTransformer.sample (transformers.py:294-369) with cached_forward (:190-287) and sample_from_logits fused
+ * into one device-side loop (no host sync per token).
+ *   partial [B,H,W,D] int64 (prefix used when start_h/start_w > 0), cond [B,cond_len] int64 or NULL (zeros),
+ *   top_k_host[D] / top_p_host[D]: per-depth settings (HOST arrays, already clamped like :314-330),
+ *   noise (nullable): per-token Exp(1) draws, token t (= the t-th *sampled* (h,w,d) in raster order) at
+ *   noise + t*noise_stride, each [B,V] f32; NULL -> q = 1,
+ *   logits_out (nullable) [n_tokens,B,V] f32 receives every step's logits (teacher-forcing / parity tests),
+ *   force_codes (nullable) [B,H,W,D] int64: teacher forcing -- logits are computed and (optionally) dumped but
+ *   the code written back is force_codes' (so the step-parity protocol of SURVEY.md 8c can be run),
+ *   out_codes [B,H,W,D] int64. */
+int rqb200_ar_sample(rqb200_ar* h, const int64_t* partial, const int64_t* cond, int B, int start_h, int start_w,
+                     float temperature, const int32_t* top_k_host, const float* top_p_host, const float* noise,
+                     int64_t noise_stride, float* logits_out, const int64_t* force_codes, int64_t* out_codes,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* number of kernels the last rqb200_ar_sample call launched (bench.py's gpu_launches) */
+int64_t rqb200_ar_last_launches(const rqb200_ar* h);
+
+/* ------------------------------------------------------------------------------------------------ P2
+ * RQVAE encode / decode (rqvae/models/rqvae/rqvae.py:80-109; modules.py:73-98,171-202; layers.py). */
+typedef struct rqb200_vae_config {
+    int32_t ch, n_levels, ch_mult[8], num_res_blocks;
+    int32_t n_attn_res, attn_resolutions[8];
+    int32_t resolution, z_channels, embed_dim, in_channels, out_ch;
+    int32_t codebook_size, depth;     /* K, D */
+    int32_t mode;                     /* RQB200_MODE_*: EXACT = f32 conv weights, FAST = f16 conv weights */
+} rqb200_vae_config;
+
+typedef struct rqb200_vae rqb200_vae;
+
+rqb200_vae* rqb200_vae_create(const rqb200_vae_config* cfg);
+void rqb200_vae_destroy(rqb200_vae* h);
+/* register one tensor under its reference state_dict key.  Conv weights must be passed
+ * re-laid-out as [Cout,KH,KW,Cin] (OHWI) in the engine's weight dtype; everything else f32 as stored. */
+int rqb200_vae_set_tensor(rqb200_vae* h, const char* key, const void* ptr, int dtype, int64_t numel);
+/* resolves every layer of encoder+decoder against the registered tensors; fails listing the first missing key */
+int rqb200_vae_finalize(rqb200_vae* h);
+size_t rqb200_vae_workspace_bytes(const rqb200_vae* h, int B);
+/* RQVAE.decode (rqvae.py:85-89): z_q [B,h,w,embed_dim] f32 NHWC -> out [B,out_ch,R,R] f32 NCHW */
+int rqb200_vae_decode(rqb200_vae* h, const float* z_q, int B, float* out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* RQVAE.decode_code (rqvae.py:105-109): codes [B,h,w,D] int64 -> out NCHW */
+int rqb200_vae_decode_code(rqb200_vae* h, const int64_t* codes, int B, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* RQVAE.encode (rqvae.py:80-83): x [B,in_channels,R,R] f32 NCHW -> z_e [B,h,w,embed_dim] f32 NHWC */
+int rqb200_vae_encode(rqb200_vae* h, const float* x, int B, float* z_e, void* workspace, size_t workspace_bytes,
+                      void* stream);
+int64_t rqb200_vae_last_launches(const rqb200_vae* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RQB200_H */

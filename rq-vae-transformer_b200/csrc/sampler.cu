@@ -1,0 +1,259 @@
+// P3 epilogue -- sample_from_logits as ONE kernel per token, no host sync.
+//
+// Replaces (reference, rqvae/utils/utils.py): top_k_logits :60-64 (torch.topk + threshold mask, ties >= k-th value
+// kept), the NaN check :103-105 (a device->host sync per token in the reference), F.softmax :108, top_p_probs :67-79
+// (torch.sort + cumsum + shifted `>=` mask + scatter + renormalise) and torch.multinomial :114, which for one draw is
+// argmax(probs / q), q ~ Exp(1) (aten: multinomial_with_replacement is NOT taken for n_sample == 1) -- the caller
+// passes the identical q tensor, so the draw is RNG-stream identical to the reference.
+//
+// One CTA (1024 threads) per row; the row (V <= 16384 fp32) is staged once in shared memory.
+//   1. x = logit / T                                  (true division, like `logits / temperature`)
+//   2. k-th largest by 4-pass 8-bit radix select on order-preserving uint keys (exact value, no sort) ; x < kth -> -inf
+//   3. NaN -> -inf ; softmax: m = max, e = exp(x - m), s = sum e, p = e / s
+//   4. top-p (only when p < 1; for p >= 1 the reference's branch removes nothing but a tail of total mass < 2^-24,
+//      see DESIGN.md "sampler short-circuit"): compact the survivors, bitonic sort descending (ties: lower index
+//      first), inclusive prefix sum accumulated in fp64 and rounded to fp32 per element (ATen's CPU cumsum uses a
+//      double accumulator for float), cut after the first position whose cumulative mass >= p, renormalise by the
+//      kept mass.
+//   5. out = argmax_i p_i / q_i, first index on ties.
+#include "common.cuh"
+
+namespace rqb {
+
+constexpr int SMP_THREADS = 1024;
+constexpr int SMP_MAXV = 16384;
+
+__device__ __forceinline__ uint32_t f2key(float f) {   // monotone: larger float -> larger key
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+struct SortItem {
+    float p;
+    int idx;
+};
+__device__ __forceinline__ bool item_before(const SortItem& a, const SortItem& b) {   // descending p, then ascending idx
+    return (a.p > b.p) || (a.p == b.p && a.idx < b.idx);
+}
+
+__global__ void __launch_bounds__(SMP_THREADS, 1)
+sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise, int V, float temperature, int top_k,
+              float top_p, int64_t* __restrict__ out_idx, const int64_t* __restrict__ force, int64_t out_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);                       // [V]   scaled logits, later probabilities
+    SortItem* items = reinterpret_cast<SortItem*>(xs + V);                // [Vpad] only touched when top_p < 1
+    __shared__ unsigned int hist[256];
+    __shared__ float red[33];
+    __shared__ int redi[33];
+    __shared__ unsigned int sel_prefix, sel_remaining, n_surv;
+    __shared__ double scan_carry[33];
+    __shared__ int cut_pos;
+    __shared__ float kept_mass;
+
+    const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const float* lg = logits + (int64_t)row * V;
+
+    if (force != nullptr) {   // teacher forcing: emit the forced code, skip the work
+        if (t == 0) out_idx[(int64_t)row * out_stride] = force[(int64_t)row * out_stride];
+        return;
+    }
+
+    for (int i = t; i < V; i += SMP_THREADS) xs[i] = lg[i] / temperature;
+    __syncthreads();
+
+    // ---- 2. top-k threshold by radix select (k-th largest key)
+    if (top_k > 0 && top_k < V) {
+        if (t == 0) { sel_prefix = 0u; sel_remaining = (unsigned)top_k; }
+        for (int pass = 3; pass >= 0; pass--) {
+            for (int i = t; i < 256; i += SMP_THREADS) hist[i] = 0u;
+            __syncthreads();
+            const int shift = pass * 8;
+            const unsigned int prefix = sel_prefix;
+            const unsigned int himask = (pass == 3) ? 0u : (0xffffffffu << (shift + 8));
+            for (int i = t; i < V; i += SMP_THREADS) {
+                uint32_t k = f2key(xs[i]);
+                if ((k & himask) == (prefix & himask)) atomicAdd(&hist[(k >> shift) & 0xffu], 1u);
+            }
+            __syncthreads();
+            if (t == 0) {
+                unsigned int rem = sel_remaining, b = 255;
+                for (;; b--) {            // walk buckets from the largest digit down
+                    unsigned int c = hist[b];
+                    if (c >= rem) break;
+                    rem -= c;
+                    if (b == 0) break;
+                }
+                sel_prefix = prefix | (b << shift);
+                sel_remaining = rem;
+            }
+            __syncthreads();
+        }
+        const float kth = key2f(sel_prefix);
+        for (int i = t; i < V; i += SMP_THREADS) {
+            float v = xs[i];
+            if (v < kth) xs[i] = -INFINITY;            // out[out < v[:, [-1]]] = -inf  (utils.py:63)
+        }
+        __syncthreads();
+    }
+
+    // ---- 3. NaN -> -inf, softmax
+    float m = -INFINITY;
+    for (int i = t; i < V; i += SMP_THREADS) {
+        float v = xs[i];
+        if (v != v) { v = -INFINITY; xs[i] = v; }
+        m = fmaxf(m, v);
+    }
+    m = block_max(m, red);
+    float ssum = 0.f;
+    for (int i = t; i < V; i += SMP_THREADS) {
+        float e = expf(xs[i] - m);
+        xs[i] = e;
+        ssum += e;
+    }
+    ssum = block_sum(ssum, red);
+    __syncthreads();
+    for (int i = t; i < V; i += SMP_THREADS) xs[i] = xs[i] / ssum;
+    __syncthreads();
+
+    // ---- 4. top-p
+    if (top_p < 1.0f) {
+        if (t == 0) n_surv = 0u;
+        __syncthreads();
+        // compact survivors (p > 0); order is irrelevant, the sort fixes it
+        for (int base = 0; base < V; base += SMP_THREADS) {
+            int i = base + t;
+            float p = (i < V) ? xs[i] : 0.f;
+            bool alive = p > 0.f;
+            unsigned bal = __ballot_sync(0xffffffffu, alive);
+            unsigned wbase = 0;
+            if (lane == 0 && bal) wbase = atomicAdd(&n_surv, (unsigned)__popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (alive) {
+                int pos = wbase + __popc(bal & ((1u << lane) - 1u));
+                items[pos].p = p;
+                items[pos].idx = i;
+            }
+        }
+        __syncthreads();
+        const int ns = (int)n_surv;
+        int npad = 1;
+        while (npad < ns) npad <<= 1;
+        for (int i = ns + t; i < npad; i += SMP_THREADS) { items[i].p = -1.f; items[i].idx = 0x7fffffff; }
+        __syncthreads();
+        for (int k = 2; k <= npad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = t; i < npad; i += SMP_THREADS) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        SortItem a = items[i], b = items[ixj];
+                        bool up = ((i & k) == 0);               // "up" block: a must come before b
+                        bool swap = up ? item_before(b, a) : item_before(a, b);
+                        if (swap) { items[i] = b; items[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // inclusive scan in fp64 (chunked: each thread owns a contiguous run), rounded to fp32 per element
+        const int per = (ns + SMP_THREADS - 1) / SMP_THREADS;
+        const int lo = min(t * per, ns), hi = min(lo + per, ns);
+        double local = 0.0;
+        for (int i = lo; i < hi; i++) local += (double)items[i].p;
+        double incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) scan_carry[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            double c = scan_carry[lane];
+            double ci = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double up = __shfl_up_sync(0xffffffffu, ci, o);
+                if (lane >= o) ci += up;
+            }
+            scan_carry[lane] = ci - c;                           // exclusive warp offsets
+        }
+        if (t == 0) cut_pos = ns - 1;
+        __syncthreads();
+        double run = scan_carry[wid] + (incl - local);
+        for (int i = lo; i < hi; i++) {
+            run += (double)items[i].p;
+            if ((float)run >= top_p) { atomicMin(&cut_pos, i); break; }   // first position with cum >= p is the last one kept
+        }
+        __syncthreads();
+        const int cut = cut_pos;
+        // kept mass: sum of the ORIGINAL-order probabilities that survive == torch.sum(probs) after masked_fill
+        for (int i = cut + 1 + t; i < ns; i += SMP_THREADS) xs[items[i].idx] = 0.f;
+        __syncthreads();
+        float km = 0.f;
+        for (int i = t; i < V; i += SMP_THREADS) km += xs[i];
+        km = block_sum(km, red);
+        if (t == 0) kept_mass = km;
+        __syncthreads();
+        const float kmv = kept_mass;
+        for (int i = t; i < V; i += SMP_THREADS) xs[i] = xs[i] / kmv;
+        __syncthreads();
+    }
+
+    // ---- 5. argmax p/q (first index on ties)
+    float best = -INFINITY;
+    int besti = 0x7fffffff;
+    const float* qr = qnoise ? qnoise + (int64_t)row * V : nullptr;
+    for (int i = t; i < V; i += SMP_THREADS) {
+        float r = qr ? xs[i] / qr[i] : xs[i];
+        if (r > best || (r == best && i < besti)) { best = r; besti = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (lane == 0) { red[wid] = best; redi[wid] = besti; }
+    __syncthreads();
+    if (wid == 0) {
+        best = red[lane];
+        besti = redi[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) out_idx[(int64_t)row * out_stride] = (besti == 0x7fffffff) ? 0 : besti;
+    }
+}
+
+// out_stride: distance (in int64 elements) between consecutive rows' outputs -- lets the AR loop write straight into
+// codes[b, h, w, d] (stride H*W*D).  force (nullable) uses the same addressing.
+int launch_sample(const float* logits, const float* q, int B, int V, float temperature, int top_k, float top_p,
+                  int64_t* out_idx, const int64_t* force, int64_t out_stride, cudaStream_t st) {
+    if (B <= 0) return B == 0 ? 0 : fail(RQB200_EINVAL, "sample: B < 0");
+    if (V <= 0 || V > SMP_MAXV) return fail(RQB200_EINVAL, "sample: V must be in [1,16384]");
+    if (!(temperature > 0.f)) return fail(RQB200_EINVAL, "sample: temperature must be > 0");
+    int vpad = 1;
+    while (vpad < V) vpad <<= 1;
+    size_t smem = (size_t)V * sizeof(float) + (top_p < 1.0f ? (size_t)vpad * sizeof(SortItem) : 0);
+    static size_t attr = 0;
+    if (smem > attr) {
+        RQB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMP_MAXV * 12)));
+        attr = SMP_MAXV * 12;
+    }
+    sample_kernel<<<B, SMP_THREADS, smem, st>>>(logits, q, V, temperature, top_k, top_p, out_idx, force, out_stride);
+    return check_launch("sample_logits");
+}
+
+}  // namespace rqb
+
+extern "C" int rqb200_sample_logits(const float* logits, const float* q, int B, int V, float temperature, int top_k,
+                                    float top_p, int64_t* out_idx, void* stream) {
+    return rqb::launch_sample(logits, q, B, V, temperature, top_k, top_p, out_idx, nullptr, 1, (cudaStream_t)stream);
+}

@@ -1,0 +1,289 @@
+"""RQTransformer -- host-side mirror of rqvae/models/rqtransformer/transformers.py:34-369 over the native AR engine.
+
+Boundary kept: constructor from an ``RQTransformerConfig``-shaped object, parameter names
+(state_dict layout A.3), ``sample`` :294-307 (same signature; ``fast``/``cached``/``is_tqdm``/``desc`` accepted),
+``cached_forward`` :191, ``init_cache`` :289, ``get_block_size``, attributes ``block_size`` / ``block_size_cond`` /
+``vocab_size``.  The (h,w,d) loop, KV caches, embedding glue, classifier and ``sample_from_logits`` all run inside
+``rqb200_ar_sample`` (csrc/ar_engine.cu): one native call per ``sample``, no per-token host work.
+
+Arithmetic tiers: ``amp=False`` -> 'exact' (fp32 weights/activations, FFMA -- the tier the bit-exact-indices gate is
+defined on); ``amp=True`` -> 'fast' (bf16 weights on tcgen05 tensor cores, fp32 accumulate; the reference's own amp
+path is fp16 autocast).  ``self.precision`` ('exact' | 'fast') or RQB200_PRECISION overrides the ``amp`` mapping."""
+import ctypes as C
+from collections import OrderedDict
+from itertools import product
+
+import torch
+import torch.nn as nn
+
+from ... import _native as N
+from ..interfaces import Stage2Model
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError("rqb200: parameter holder -- compute runs in the native engine (RQTransformer.sample)")
+
+
+class _Attn(_Holder):
+    def __init__(self, E, n_head, bias):
+        super().__init__()
+        self.key, self.query, self.value = nn.Linear(E, E, bias=bias), nn.Linear(E, E, bias=bias), nn.Linear(E, E, bias=bias)
+        self.proj = nn.Linear(E, E, bias)
+        self.n_head = n_head
+
+
+class _Block(_Holder):
+    def __init__(self, cfg):
+        super().__init__()
+        E = cfg.embed_dim
+        assert E % cfg.n_head == 0
+        self.ln1, self.ln2 = nn.LayerNorm(E), nn.LayerNorm(E)
+        self.attn = _Attn(E, cfg.n_head, cfg.attn_bias)
+        # indices 0 / 2 carry the weights (attentions.py:117-122); 1 / 3 are GELU / dropout in the reference
+        self.mlp = nn.Sequential(nn.Linear(E, 4 * E, bias=cfg.mlp_bias), nn.Identity(), nn.Linear(4 * E, E, bias=cfg.mlp_bias),
+                                 nn.Identity())
+        if cfg.gelu != "v1":
+            raise NotImplementedError("rqb200: only the exact-erf GELU ('v1') is implemented (all shipped configs)")
+
+
+class _Stack(_Holder):
+    def __init__(self, cfg):
+        super().__init__()
+        self.blocks = nn.ModuleList([_Block(cfg.block) for _ in range(cfg.n_layer)])
+
+
+class RQTransformer(Stage2Model):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config = config.copy()
+        if len(config.block_size) != 3:
+            raise ValueError("incompatible block size")
+        self.block_size = torch.Size(config.block_size)
+        if isinstance(config.vocab_size, int):
+            config.vocab_size = [config.vocab_size] * config.block_size[2]
+        vs = list(config.vocab_size)
+        if not (config.shared_tok_emb and config.shared_cls_emb and config.input_emb_vqvae and config.head_emb_vqvae
+                and config.cumsum_depth_ctx):
+            raise NotImplementedError("rqb200: only the shipped configuration family is implemented (shared_tok_emb, "
+                                      "shared_cls_emb, input_emb_vqvae, head_emb_vqvae, cumsum_depth_ctx all true)")
+        assert [vs[0]] * len(vs) == vs
+        self.vocab_size = vs
+        E = config.embed_dim
+        self.vocab_size_cond = max(config.vocab_size_cond, 1)
+        self.block_size_cond = max(config.block_size_cond, 1)
+        assert not (self.block_size_cond > 1 and self.vocab_size_cond == 1)
+        self.cond_emb = nn.Embedding(self.vocab_size_cond, E)
+        self.tok_emb = None
+        self.input_mlp = nn.Linear(config.input_embed_dim, E)
+        self.head_mlp = nn.Linear(config.input_embed_dim, E)
+        self.pos_emb_cond = nn.Parameter(torch.zeros(1, self.block_size_cond, E))
+        self.pos_emb_hw = nn.Parameter(torch.zeros(1, self.block_size[0] * self.block_size[1], E))
+        self.pos_emb_d = nn.Parameter(torch.zeros(1, self.block_size[2], E))
+        for p in (self.pos_emb_cond, self.pos_emb_hw, self.pos_emb_d):
+            p.data.normal_(mean=0.0, std=0.02)
+        self.body_transformer = _Stack(config.body)
+        self.head_transformer = _Stack(config.head)
+        self.classifier = nn.Sequential(OrderedDict([("layer_norm", nn.LayerNorm(E)), ("linear", nn.Linear(E, vs[0]))]))
+        if config.block_size_cond > 1:
+            self.cond_classifier = nn.Sequential(OrderedDict([("layer_norm", nn.LayerNorm(E)),
+                                                              ("linear", nn.Linear(E, config.vocab_size_cond))]))
+        self.precision = None
+        self._eng = {}
+        self._cache = None
+        self.last_launches = 0
+
+    # ------------------------------------------------------------------ native engine plumbing
+    def _invalidate_native(self):
+        for e in self._eng.values():
+            N.lib().rqb200_ar_destroy(e["handle"])
+        self._eng = {}
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate_native()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._invalidate_native()
+        return super().load_state_dict(*a, **k)
+
+    def __del__(self):
+        try:
+            self._invalidate_native()
+        except Exception:
+            pass
+
+    def _mode(self, amp):
+        p = self.precision or N.default_precision()
+        if p == "auto":
+            p = "fast" if amp else "exact"
+        return N.MODE_FAST if p == "fast" else N.MODE_EXACT
+
+    @staticmethod
+    def _codebook_of(model_aux, depth):
+        """the [K,C] table behind model_aux.get_code_emb_with_depth (transformers.py:109-111)"""
+        q = getattr(model_aux, "quantizer", None)
+        if q is not None and hasattr(q, "_shared_table"):
+            return q._shared_table()
+        if q is not None and getattr(q, "shared_codebook", False):
+            return q.codebooks[0].weight[:-1]
+        raise NotImplementedError("rqb200: model_aux must be an RQ-VAE with a shared codebook")
+
+    def _engine(self, codebook, mode):
+        dev = self.pos_emb_hw.device
+        key = (str(dev), mode, codebook.data_ptr())
+        if key in self._eng:
+            return self._eng[key]
+        N.require_cuda(self.pos_emb_hw, codebook)
+        L = N.lib()
+        wdt = torch.bfloat16 if mode == N.MODE_FAST else torch.float32
+        keep = []
+
+        def f32(t):
+            t = t.detach().float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def wt(t):
+            t = t.detach().to(wdt).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def blocks(stack):
+            arr = (N.BlockWeights * len(stack.blocks))()
+            for i, b in enumerate(stack.blocks):
+                a = b.attn
+                arr[i].wqkv = wt(torch.cat([a.query.weight, a.key.weight, a.value.weight], 0))
+                arr[i].bqkv = f32(torch.cat([a.query.bias, a.key.bias, a.value.bias], 0))
+                arr[i].wproj, arr[i].bproj = wt(a.proj.weight), f32(a.proj.bias)
+                arr[i].w1, arr[i].b1 = wt(b.mlp[0].weight), f32(b.mlp[0].bias)
+                arr[i].w2, arr[i].b2 = wt(b.mlp[2].weight), f32(b.mlp[2].bias)
+                arr[i].ln1_w, arr[i].ln1_b = f32(b.ln1.weight), f32(b.ln1.bias)
+                arr[i].ln2_w, arr[i].ln2_b = f32(b.ln2.weight), f32(b.ln2.bias)
+            return arr
+
+        cfg = N.ArConfig()
+        c = self.config
+        cfg.embed_dim, cfg.n_head = c.embed_dim, c.body.block.n_head
+        cfg.n_body, cfg.n_head_layers = len(self.body_transformer.blocks), len(self.head_transformer.blocks)
+        cfg.vocab, cfg.H, cfg.W, cfg.D = self.vocab_size[0], self.block_size[0], self.block_size[1], self.block_size[2]
+        cfg.vocab_cond, cfg.cond_len = self.vocab_size_cond, self.block_size_cond
+        cfg.code_dim, cfg.codebook_size = codebook.shape[1], codebook.shape[0]
+        cfg.mode, cfg.weight_dtype = mode, N._DT[wdt]
+        if c.head.block.n_head != c.body.block.n_head:
+            raise NotImplementedError("rqb200: body and head stacks must share n_head")
+        w = N.ArWeights()
+        w.pos_emb_cond, w.pos_emb_hw, w.pos_emb_d = f32(self.pos_emb_cond), f32(self.pos_emb_hw), f32(self.pos_emb_d)
+        w.cond_emb = f32(self.cond_emb.weight)
+        w.w_in, w.b_in = wt(self.input_mlp.weight), f32(self.input_mlp.bias)
+        w.w_head, w.b_head = wt(self.head_mlp.weight), f32(self.head_mlp.bias)
+        w.w_cls, w.b_cls = wt(self.classifier.linear.weight), f32(self.classifier.linear.bias)
+        w.cls_ln_w, w.cls_ln_b = f32(self.classifier.layer_norm.weight), f32(self.classifier.layer_norm.bias)
+        w.codebook = f32(codebook)
+        body, head = blocks(self.body_transformer), blocks(self.head_transformer)
+        w.body, w.head = C.cast(body, C.POINTER(N.BlockWeights)), C.cast(head, C.POINTER(N.BlockWeights))
+        handle = L.rqb200_ar_create(C.byref(cfg), C.byref(w))
+        if not handle:
+            raise N.NativeError("rqb200_ar_create: " + L.rqb200_last_error().decode())
+        eng = {"handle": handle, "keep": keep, "ws": None}
+        self._eng[key] = eng
+        return eng
+
+    # ------------------------------------------------------------------ reference surface
+    def init_cache(self):
+        """transformers.py:289-292 -- KV state lives inside one native call; nothing persists between calls"""
+        self._cache = {"spatial_ctx_hw": None}
+
+    def _lists(self, top_k, top_p):
+        D = self.block_size[2]
+        V = self.vocab_size
+        if top_k is None:
+            ks = [V[i] for i in range(D)]
+        elif isinstance(top_k, int):
+            ks = [min(top_k, V[i]) for i in range(D)]
+        elif len(top_k) == 1:
+            ks = [min(top_k[0], V[i]) for i in range(D)]
+        else:
+            ks = [min(top_k[i], V[i]) for i in range(D)]
+        if top_p is None:
+            ps = [1.0] * D
+        elif isinstance(top_p, float):
+            ps = [min(top_p, 1.0)] * D
+        elif len(top_p) == 1:
+            ps = [min(top_p[0], 1.0)] * D
+        else:
+            ps = [min(top_p[i], 1.0) for i in range(D)]
+        return ks, ps
+
+    @torch.no_grad()
+    def _native_sample(self, partial, model_aux, cond, start_loc, temperature, top_k, top_p, amp, noise=None,
+                       return_logits=False, force_codes=None):
+        H, W, D = self.block_size
+        B = partial.shape[0]
+        dev = self.pos_emb_hw.device
+        N.require_cuda(partial, cond, self.pos_emb_hw)
+        ks, ps = self._lists(top_k, top_p)
+        eng = self._engine(self._codebook_of(model_aux, D), self._mode(amp))
+        partial = partial.to(torch.int64).contiguous()
+        cond_t = None if cond is None else cond.reshape(B, self.block_size_cond).to(torch.int64).contiguous()
+        idx0 = start_loc[0] * W + start_loc[1]
+        n_tok = max(H * W - idx0, 0) * D
+        V = self.vocab_size[0]
+        with torch.cuda.device(dev):
+            if noise is None:
+                # one exponential_ per token, in (h,w,d) order: the draws torch.multinomial would make (utils.py:114)
+                noise = torch.empty(n_tok, B, V, dtype=torch.float32, device=dev)
+                for t in range(n_tok):
+                    noise[t].exponential_(1)
+            elif noise is False:
+                noise = None
+            logits = torch.empty(n_tok, B, V, dtype=torch.float32, device=dev) if return_logits else None
+            out = torch.empty_like(partial)
+            need = N.lib().rqb200_ar_workspace_bytes(eng["handle"], B)
+            if eng["ws"] is None or eng["ws"].numel() < need:
+                eng["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+            kk = (C.c_int32 * D)(*[int(k) for k in ks])
+            pp = (C.c_float * D)(*[float(p) for p in ps])
+            fc = None if force_codes is None else force_codes.to(torch.int64).contiguous()
+            N.check(N.lib().rqb200_ar_sample(eng["handle"], N.ptr(partial), N.ptr(cond_t), B, int(start_loc[0]),
+                                             int(start_loc[1]), float(temperature), kk, pp, N.ptr(noise),
+                                             0 if noise is None else B * V, N.ptr(logits), N.ptr(fc), N.ptr(out),
+                                             N.ptr(eng["ws"]), eng["ws"].numel(), N.stream_ptr(dev)), "ar_sample")
+        self.last_launches = N.lib().rqb200_ar_last_launches(eng["handle"])
+        N.launch_count["total"] += self.last_launches
+        return (out, logits) if return_logits else out
+
+    @torch.no_grad()
+    def sample(self, partial_sample, model_aux=None, cond=None, start_loc=(0, 0), temperature=1.0, top_k=None, top_p=None,
+               amp=False, cached=True, is_tqdm=False, desc="Sampling", fast=True):
+        """transformers.py:294-369.  Returns LongTensor [B,H,W,D]; ``partial_sample`` is not modified."""
+        assert self.block_size == partial_sample.shape[1:]
+        self.init_cache()
+        out = self._native_sample(partial_sample, model_aux, cond, start_loc, temperature, top_k, top_p, amp)
+        self.init_cache()
+        return out
+
+    @torch.no_grad()
+    def cached_forward(self, xs, model_aux=None, cond=None, amp=False, sample_loc=(0, 0, 0)):
+        """transformers.py:190-287 -- logits [B,V] for one (h,w,d).  Stateless re-evaluation: the prefix in ``xs`` is
+        teacher-forced through the native loop and the requested step's logits are returned."""
+        h, w, d = sample_loc
+        H, W, D = self.block_size
+        B = xs.shape[0]
+        full = torch.zeros(B, H, W, D, dtype=torch.int64, device=xs.device)
+        full[:, :xs.shape[1]] = xs
+        _, logits = self._native_sample(full, model_aux, cond, (0, 0), 1.0, None, None, amp, noise=False,
+                                        return_logits=True, force_codes=full)
+        return logits[(h * W + w) * D + d]
+
+    def forward(self, xs, model_aux=None, cond=None, amp=False):
+        """transformers.py:113-188 -- teacher-forced logits [B,H,W,D,V] (cond_len == 1 return convention)."""
+        if self.block_size_cond > 1:
+            raise NotImplementedError("rqb200: cond_logits for cond_len > 1 are not produced by the sampling engine")
+        B, H, W, D = xs.shape
+        _, logits = self._native_sample(xs, model_aux, cond, (0, 0), 1.0, None, None, amp, noise=False,
+                                        return_logits=True, force_codes=xs)
+        return logits.reshape(H, W, D, B, -1).permute(3, 0, 1, 2, 4).contiguous()
+
+    def compute_loss(self, logits, targets, use_soft_target=False):
+        return torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), targets.reshape(-1))

@@ -147,6 +147,14 @@ int rqb200_vae_encode(rqb200_vae* h, const float* x, int B, float* z_e, void* wo
                       void* stream);
 int64_t rqb200_vae_last_launches(const rqb200_vae* h);
 
+/* ------------------------------------------------------------------------------------------------ diagnostics
+ * Single-kernel entry points used by tests/ and bench.py's roofline leg; not part of the reference-facing surface.
+ * rqb200_dbg_gemm_tc: one launch of the tcgen05 weight-streaming GEMM (csrc/gemm_tc.cu):
+ *   out[b, n] = act(sum_k W[n,k] X[b,k] + bias[n]) (+ residual[b,n]);  W [N_out,K] bf16, X [B,K] bf16;
+ *   splits > 1: partial [splits,B,N_out] f32 receives the per-split sums instead (no act / residual). */
+int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out,
+                       int out_is_bf16, int gelu, float* partial, int N_out, int K, int B, int splits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,5 +14,5 @@ for f in *.cu; do
   fi
   OBJS="$OBJS $f.o"
 done
-$NVCC -shared -o librqb200.so $OBJS -lcudart -lcuda
+$NVCC -shared -o librqb200.so $OBJS -lcudart
 echo "built $(pwd)/librqb200.so"

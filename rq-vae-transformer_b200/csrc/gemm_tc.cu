@@ -1,0 +1,255 @@
+// P3 "fast" tier workhorse -- weight-streaming skinny GEMM on tcgen05 tensor cores.
+//
+//   D[n, b] = sum_k W[n, k] * X[b, k]            W: [N_out, K] bf16 (nn.Linear layout), X: [B, K] bf16, D fp32 in TMEM
+//
+// Replaces every nn.Linear of the cached AR step (reference: attentions.py:69-71,99,117-122; transformers.py:94) at
+// M = batch rows.  At B <= 256 these GEMMs are HBM-bound on the *weights* (SURVEY.md finding 5), so the kernel is laid
+// out as a weight streamer with the operands SWAPPED: the weight tile is the UMMA "A" operand (M = 128 output features
+// per CTA, K-major -- exactly the [out,in] row-major layout checkpoints already have, no transpose), the activations are
+// the "B" operand (N = batch padded to 16).  One elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 TMEM);
+// weights and activations arrive through TMA (SWIZZLE_128B, 64-element K slabs) into a STAGES-deep mbarrier ring.
+//
+// Programmatic dependent launch: weight tiles do not depend on the previous kernel, so the producer warp fills the ring
+// with weights BEFORE griddepcontrol.wait; only the activation loads, the epilogue's residual reads and all stores wait
+// for the upstream kernel.  Back-to-back kernels of the per-token chain thereby keep HBM busy across kernel boundaries.
+//
+// Split-K (blockIdx.x = tile * splits + split) spreads the N_out/128 tiles of the narrow GEMMs (proj, fc2: 12 tiles at
+// E = 1536) over all 148 SMs; partial tiles go to an fp32 workspace [split][B][N_out] and are summed in a FIXED order by
+// the consumer kernel (ln_reduce) -> deterministic, no atomics.
+#include "kernels.h"
+#include "tc_common.cuh"
+#include <cudaTypedefs.h>
+
+namespace rqb {
+
+static int get_encode_fn(PFN_cuTensorMapEncodeTiled_v12000* fn) {
+    static PFN_cuTensorMapEncodeTiled_v12000 cached = nullptr;
+    if (!cached) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            return fail(RQB200_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+        cached = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    *fn = cached;
+    return 0;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes_log2, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+    PFN_cuTensorMapEncodeTiled_v12000 enc;
+    RQB_TRY(get_encode_fn(&enc));
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = elem_bytes_log2 == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RQB200_ECUDA, "cuTensorMapEncodeTiled(2d) failed: " + std::to_string((int)r));
+    return 0;
+}
+
+int make_tmap_4d_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_c,
+                      uint32_t box_w, uint32_t box_h, uint32_t box_b) {
+    PFN_cuTensorMapEncodeTiled_v12000 enc;
+    RQB_TRY(get_encode_fn(&enc));
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[4] = {box_c, box_w, box_h, box_b};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RQB200_ECUDA, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string((int)r));
+    return 0;
+}
+
+constexpr int GT_THREADS = 192;
+constexpr int GT_A_BYTES = 128 * 64 * 2;     // 128 output features x 64 k, bf16
+
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GT_THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, GemmTcParams p) {
+    constexpr int B_BYTES = BN * 64 * 2;
+    constexpr int STAGE_BYTES = GT_A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+    const int nkb_total = p.K / 64;
+    const int kb0 = (int)((int64_t)nkb_total * split / p.splits), kb1 = (int)((int64_t)nkb_total * (split + 1) / p.splits);
+    const int nkb = kb1 - kb0;
+
+    tc::pdl_launch_dependents();             // let the next kernel of the chain start its own weight prefetch
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmW);
+        tc::prefetch_tmap(&tmX);
+        for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer.  Weights first (independent of the upstream kernel), then wait, then activations.
+            const int pre = nkb < STAGES ? nkb : STAGES;
+            for (int i = 0; i < pre; i++) {
+                tc::mbar_expect_tx(&full[i], STAGE_BYTES);
+                tc::tma_load_2d(smem + i * STAGE_BYTES, &tmW, &full[i], (kb0 + i) * 64, tile * 128, tc::L2_EVICT_FIRST);
+            }
+            tc::pdl_wait();
+            for (int i = 0; i < pre; i++)
+                tc::tma_load_2d(smem + i * STAGE_BYTES + GT_A_BYTES, &tmX, &full[i], (kb0 + i) * 64, 0, tc::L2_EVICT_LAST);
+            for (int i = pre; i < nkb; i++) {
+                const int s = i % STAGES;
+                tc::mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+                tc::mbar_expect_tx(&full[s], STAGE_BYTES);
+                tc::tma_load_2d(smem + s * STAGE_BYTES, &tmW, &full[s], (kb0 + i) * 64, tile * 128, tc::L2_EVICT_FIRST);
+                tc::tma_load_2d(smem + s * STAGE_BYTES + GT_A_BYTES, &tmX, &full[s], (kb0 + i) * 64, 0, tc::L2_EVICT_LAST);
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        constexpr uint32_t idesc = tc::umma_idesc(128, BN, 1 /*bf16*/);
+        for (int i = 0; i < nkb; i++) {
+            const int s = i % STAGES;
+            tc::mbar_wait(&full[s], (i / STAGES) & 1);
+            tc::tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a = tc::smem_u32(smem + s * STAGE_BYTES), b = a + GT_A_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    tc::umma_f16(tmem_base, tc::umma_desc_k128(a + j * 32), tc::umma_desc_k128(b + j * 32), idesc,
+                                 (i > 0 || j > 0) ? 1u : 0u);
+                tc::umma_commit(&empty[s]);                    // frees the ring slot once these MMAs have read it
+                if (i == nkb - 1) tc::umma_commit(tmem_full);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4, thread <-> one output feature n, all batch columns
+        tc::pdl_wait();
+        const int q = warp & 3;
+        const int n = tile * 128 + q * 32 + lane;
+        tc::mbar_wait(tmem_full, 0);
+        tc::tc_fence_after();
+        const bool nvalid = n < p.N_out;
+        const float bias = (p.bias != nullptr && nvalid && (p.mode != GT_PARTIAL || split == 0)) ? p.bias[n] : 0.f;
+        int seg = 0, hh = 0, dd = 0, tpos = 0;
+        if (p.mode == GT_QKV) {
+            seg = n / p.E;
+            int e = n % p.E;
+            hh = e >> 6;
+            dd = e & 63;
+            tpos = p.t_ptr ? *p.t_ptr : p.t_host;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tc::tmem_ld_wait();
+            if (!nvalid) continue;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int b = c0 + i;
+                if (b >= p.B) break;
+                float v = __uint_as_float(r[i]) + bias;
+                switch (p.mode) {
+                    case GT_F32:
+                        if (p.residual) v += p.residual[(int64_t)b * p.ld_out + n];
+                        reinterpret_cast<float*>(p.out)[(int64_t)b * p.ld_out + n] = v;
+                        break;
+                    case GT_BF16:
+                        reinterpret_cast<__nv_bfloat16*>(p.out)[(int64_t)b * p.ld_out + n] = __float2bfloat16(v);
+                        break;
+                    case GT_BF16_GELU:
+                        reinterpret_cast<__nv_bfloat16*>(p.out)[(int64_t)b * p.ld_out + n] = __float2bfloat16(gelu_erf_f(v));
+                        break;
+                    case GT_PARTIAL:
+                        p.partial[((int64_t)split * p.B + b) * p.N_out + n] = v;
+                        break;
+                    case GT_QKV:
+                        if (seg == 0) p.q_out[(int64_t)b * p.E + hh * 64 + dd] = __float2bfloat16(v);
+                        else {
+                            __nv_bfloat16* c = seg == 1 ? p.kc : p.vc;
+                            c[(((int64_t)b * p.nh + hh) * p.Tmax + tpos) * 64 + dd] = __float2bfloat16(v);
+                        }
+                        break;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (GT_A_BYTES + BN * 128) + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        RQB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ceil_div(p.N_out, 128) * p.splits));
+    cfg.blockDim = dim3(GT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RQB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES>, tmW, tmX, p));
+    g_launches++;
+    return 0;
+}
+
+int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
+    if (p.K % 64 != 0 || p.N_out % 128 != 0) return fail(RQB200_EINVAL, "gemm_tc: need K % 64 == 0 and N_out % 128 == 0");
+    if (p.B < 1 || p.B > 256) return fail(RQB200_EINVAL, "gemm_tc: batch rows must be in [1,256]");
+    if (p.splits < 1 || p.splits > p.K / 64) return fail(RQB200_EINVAL, "gemm_tc: bad split count");
+    const int bn = gemm_tc_bn(p.B);
+    switch (bn) {
+        case 16: return launch_gemm_tc_t<16, 6>(tmW, tmX, p, pdl, st);
+        case 32: return launch_gemm_tc_t<32, 5>(tmW, tmX, p, pdl, st);
+        case 64: return launch_gemm_tc_t<64, 4>(tmW, tmX, p, pdl, st);
+        case 128: return launch_gemm_tc_t<128, 3>(tmW, tmX, p, pdl, st);
+        default: return launch_gemm_tc_t<256, 2>(tmW, tmX, p, pdl, st);
+    }
+}
+
+}  // namespace rqb
+
+// ---- diagnostic entry point (tests/test_gpu_tc.py): one GEMM through the tcgen05 kernel
+extern "C" int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out,
+                                  int out_is_bf16, int gelu, float* partial, int N_out, int K, int B, int splits,
+                                  void* stream) {
+    using namespace rqb;
+    CUtensorMap tw, tx;
+    const int bn = gemm_tc_bn(B);
+    RQB_TRY(make_tmap_2d(&tw, W_bf16, 1, (uint64_t)K, (uint64_t)N_out, (uint64_t)K * 2, 64, 128));
+    RQB_TRY(make_tmap_2d(&tx, X_bf16, 1, (uint64_t)K, (uint64_t)B, (uint64_t)K * 2, 64, (uint32_t)bn));
+    GemmTcParams p = {};
+    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits;
+    p.bias = bias; p.residual = residual; p.out = out; p.ld_out = N_out; p.partial = partial;
+    p.mode = splits > 1 ? GT_PARTIAL : (out_is_bf16 ? (gelu ? GT_BF16_GELU : GT_BF16) : GT_F32);
+    return launch_gemm_tc(tw, tx, p, false, (cudaStream_t)stream);
+}

@@ -1,5 +1,7 @@
 // internal launch prototypes (host side) shared by the engine translation units
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace rqb {
@@ -45,4 +47,23 @@ int launch_groupnorm_silu(const float* X, const float* gamma, const float* beta,
                           int C, int silu, cudaStream_t st);
 int launch_vae_attn(const float* qkv, float* out, int B, int HW, int C, cudaStream_t st);
 size_t groupnorm_ws_doubles(int B, int HW);
+
+// gemm_tc.cu -- tcgen05 weight-streaming GEMM (fast tier)
+enum GemmTcMode { GT_F32 = 0, GT_BF16 = 1, GT_BF16_GELU = 2, GT_PARTIAL = 3, GT_QKV = 4 };
+struct GemmTcParams {
+    int N_out, K, B, splits, mode;
+    const float* bias;            // [N_out] (nullable)
+    const float* residual;        // GT_F32 only: out = residual + ...   [B, ld_out]
+    void* out;                    // [B, ld_out] f32 / bf16
+    int64_t ld_out;
+    float* partial;               // GT_PARTIAL: [splits][B][N_out] f32
+    // GT_QKV: rows [0,E) -> q_out [B,E] bf16 ; [E,2E) -> kc ; [2E,3E) -> vc  (cache [B][nh][Tmax][64] bf16, row *t_ptr)
+    __nv_bfloat16 *q_out, *kc, *vc;
+    int E, nh, Tmax, t_host;
+    const int* t_ptr;
+};
+inline int gemm_tc_bn(int B) { return B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : B <= 128 ? 128 : 256; }
+int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st);
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes_log2, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 }  // namespace rqb

@@ -16,6 +16,7 @@ struct rqb200_ar {
     rqb200_ar_weights w;
     std::vector<rqb200_block_weights> body, head;
     int64_t last_launches = 0;
+    rqb::ArFast* fast = nullptr;
 };
 
 namespace rqb {
@@ -146,11 +147,20 @@ rqb200_ar* rqb200_ar_create(const rqb200_ar_config* cfg, const rqb200_ar_weights
     h->head.assign(w->head, w->head + cfg->n_head_layers);
     h->w.body = h->body.data();
     h->w.head = h->head.data();
+    if (cfg->mode == RQB200_MODE_FAST) {
+        if (cfg->weight_dtype != RQB200_BF16) { rqb::set_error("ar_create: fast tier needs bf16 weights"); delete h; return nullptr; }
+        h->fast = rqb::ar_fast_create(h->cfg, h->w, h->body.data(), h->head.data());
+        if (!h->fast) { delete h; return nullptr; }
+    }
     return h;
 }
-void rqb200_ar_destroy(rqb200_ar* h) { delete h; }
+void rqb200_ar_destroy(rqb200_ar* h) {
+    if (h && h->fast) rqb::ar_fast_destroy(h->fast);
+    delete h;
+}
 size_t rqb200_ar_workspace_bytes(const rqb200_ar* h, int B) {
     if (!h || B <= 0) return 0;
+    if (h->fast) return rqb::ar_fast_workspace_bytes(h->fast, B);
     return rqb::ar_layout(h->cfg, B, nullptr, 0, nullptr);
 }
 int rqb200_ar_sample(rqb200_ar* h, const int64_t* partial, const int64_t* cond, int B, int start_h, int start_w,
@@ -161,6 +171,13 @@ int rqb200_ar_sample(rqb200_ar* h, const int64_t* partial, const int64_t* cond, 
         return rqb::fail(RQB200_EINVAL, "ar_sample: null argument");
     if (rqb200_device_count() <= 0) return rqb::fail(RQB200_ENODEV, "ar_sample: no CUDA device");
     rqb::g_launches = 0;
+    if (h->fast) {
+        int rc = rqb::ar_fast_sample(h->fast, partial, cond, B, start_h, start_w, temperature, top_k_host, top_p_host, noise,
+                                     noise_stride, logits_out, force_codes, out_codes, workspace, workspace_bytes,
+                                     (cudaStream_t)stream);
+        h->last_launches = rqb::g_launches;
+        return rc;
+    }
     int rc = rqb::ar_sample_impl(h, partial, cond, B, start_h, start_w, temperature, top_k_host, top_p_host, noise,
                                  noise_stride, logits_out, force_codes, out_codes, workspace, workspace_bytes,
                                  (cudaStream_t)stream);

@@ -1,0 +1,518 @@
+// P3 "fast" tier -- the cached AR step as a PDL-chained, CUDA-graph-replayed sequence of sm_100a kernels.
+//
+// Same semantics as ar_engine.cu's exact tier (reference: transformers.py:190-369, attentions.py:60-142), different
+// arithmetic class: bf16 weights / activations / KV cache on tcgen05 (gemm_tc.cu), fp32 residual stream, fp32
+// LayerNorm / softmax / sampler.  What the chain looks like for one transformer block (M = batch rows):
+//
+//     ln_reduce   x += bias_prev + sum_s partial_prev[s] ; xn = LN(x) (bf16)      <- fused split-K reduction + residual
+//     gemm_tc     qkv partials = Wqkv . xn                                         (split-K, 144 CTAs)
+//     attn_fast   q,k,v = sum partials + bias ; append k,v to the bf16 cache ; softmax(q k^T/8) v -> att (bf16)
+//     gemm_tc     proj partials = Wproj . att
+//     ln_reduce   x += bproj + sum partials ; xn = LN2(x)
+//     gemm_tc     h = gelu(W1 . xn + b1) (bf16)            (direct epilogue, or split-K + act_reduce)
+//     gemm_tc     fc2 partials = W2 . h
+//
+// Every kernel starts with griddepcontrol.launch_dependents and reads upstream data only after griddepcontrol.wait, so
+// the NEXT kernel's prologue -- for the GEMMs: filling the shared-memory ring with weight tiles -- overlaps this one.
+// Position-dependent scalars (sequence index, spatial index, token counter) live in a device-side StepState that the
+// last kernel of each graph advances, so three captured graphs (cond-token body step, code-token body step, head steps
+// + sampling) are replayed for all positions without host involvement.
+#include <vector>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace rqb {
+
+template <typename... KArgs, typename... Args>
+static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RQB_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    g_launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+// x_out = x_in + bias + sum_s partial[s] (+ extra row) ; xn = LayerNorm(x_out) in bf16.  One CTA per batch row.
+__global__ void __launch_bounds__(384)
+ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int S, const float* __restrict__ bias,
+                 const float* __restrict__ extra, float* __restrict__ x_out, const float* __restrict__ g,
+                 const float* __restrict__ be, __nv_bfloat16* __restrict__ xn, int B, int E) {
+    extern __shared__ float row[];
+    __shared__ float red[33];
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int b = blockIdx.x;
+    const int E4 = E >> 2;
+    float s = 0.f;
+    for (int e4 = threadIdx.x; e4 < E4; e4 += blockDim.x) {
+        float4 v = x_in ? reinterpret_cast<const float4*>(x_in + (int64_t)b * E)[e4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) { float4 t = reinterpret_cast<const float4*>(bias)[e4]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        // split-K partials: issue the loads in batches of 4 (independent), add in a fixed order (deterministic)
+        int i = 0;
+        for (; i + 4 <= S; i += 4) {
+            float4 p0 = reinterpret_cast<const float4*>(partial + ((int64_t)(i + 0) * B + b) * E)[e4];
+            float4 p1 = reinterpret_cast<const float4*>(partial + ((int64_t)(i + 1) * B + b) * E)[e4];
+            float4 p2 = reinterpret_cast<const float4*>(partial + ((int64_t)(i + 2) * B + b) * E)[e4];
+            float4 p3 = reinterpret_cast<const float4*>(partial + ((int64_t)(i + 3) * B + b) * E)[e4];
+            v.x += p0.x; v.y += p0.y; v.z += p0.z; v.w += p0.w;
+            v.x += p1.x; v.y += p1.y; v.z += p1.z; v.w += p1.w;
+            v.x += p2.x; v.y += p2.y; v.z += p2.z; v.w += p2.w;
+            v.x += p3.x; v.y += p3.y; v.z += p3.z; v.w += p3.w;
+        }
+        for (; i < S; i++) {
+            float4 p0 = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
+            v.x += p0.x; v.y += p0.y; v.z += p0.z; v.w += p0.w;
+        }
+        if (extra) { float4 t = reinterpret_cast<const float4*>(extra)[e4]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        reinterpret_cast<float4*>(row)[e4] = v;
+        s += (v.x + v.y) + (v.z + v.w);
+        if (x_out) reinterpret_cast<float4*>(x_out + (int64_t)b * E)[e4] = v;
+    }
+    const float mean = block_sum(s, red) / (float)E;
+    float q = 0.f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) { float d = row[e] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(block_sum(q, red) / (float)E + 1e-5f);
+    if (xn)
+        for (int e = threadIdx.x; e < E; e += blockDim.x)
+            xn[(int64_t)b * E + e] = __float2bfloat16((row[e] - mean) * rstd * g[e] + be[e]);
+}
+
+// h = bf16(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K)
+__global__ void __launch_bounds__(256)
+act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, __nv_bfloat16* __restrict__ h, int B,
+                  int N) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int64_t total = (int64_t)B * N;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        int n = (int)(i % N);
+        float v = bias[n];
+        for (int s = 0; s < S; s++) v += partial[(int64_t)s * total + i];
+        h[i] = __float2bfloat16(0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)));
+    }
+}
+
+// one warp per (b, head): reduce the split-K qkv partials (+bias), append k,v at row t of the bf16 cache, attend.
+// lane <-> dims (2*lane, 2*lane+1) for q/k/v/out; lane <-> key for the scores (q and the probabilities are
+// broadcast through shared memory).  T <= 512.
+constexpr int AF_MAXT = 512;
+__global__ void __launch_bounds__(128)
+attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, __nv_bfloat16* __restrict__ kc,
+                 __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ att, int B, int E, int nh, int Tmax,
+                 const int* __restrict__ t_ptr, int t_host) {
+    __shared__ float qs[4][64];
+    __shared__ float ps[4][AF_MAXT];
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int bh = blockIdx.x * 4 + wq;
+    if (bh >= B * nh) return;
+    const int b = bh / nh, h = bh % nh;
+    const int t = t_ptr ? *t_ptr : t_host;
+    const int c = h * 64 + 2 * lane;
+    float2 q = make_float2(bqkv[c], bqkv[c + 1]);
+    float2 k = make_float2(bqkv[E + c], bqkv[E + c + 1]);
+    float2 v = make_float2(bqkv[2 * E + c], bqkv[2 * E + c + 1]);
+    for (int s = 0; s < S; s++) {
+        const float* p = part + ((int64_t)s * B + b) * 3 * E;
+        float2 a = *reinterpret_cast<const float2*>(p + c);
+        float2 bb = *reinterpret_cast<const float2*>(p + E + c);
+        float2 cc = *reinterpret_cast<const float2*>(p + 2 * E + c);
+        q.x += a.x; q.y += a.y; k.x += bb.x; k.y += bb.y; v.x += cc.x; v.y += cc.y;
+    }
+    __nv_bfloat16* kb = kc + ((int64_t)(b * nh + h) * Tmax) * 64;
+    __nv_bfloat16* vb = vc + ((int64_t)(b * nh + h) * Tmax) * 64;
+    const __nv_bfloat162 k2 = __floats2bfloat162_rn(k.x, k.y), v2 = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(kb + (int64_t)t * 64 + 2 * lane) = k2;
+    *reinterpret_cast<__nv_bfloat162*>(vb + (int64_t)t * 64 + 2 * lane) = v2;
+    // use the bf16-rounded q/k/v everywhere (what a later step reads back from the cache)
+    const float2 qf = __bfloat1622float2(__floats2bfloat162_rn(q.x, q.y)), kf = __bfloat1622float2(k2), vf = __bfloat1622float2(v2);
+    qs[wq][2 * lane] = qf.x;
+    qs[wq][2 * lane + 1] = qf.y;
+    __syncwarp();
+    const float s_new = warp_sum(qf.x * kf.x + qf.y * kf.y) * 0.125f;
+    float m = s_new;
+    for (int j = lane; j < t; j += 32) {          // scores of the cached rows
+        const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)j * 64);
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            uint4 w = kr[u];
+            const __nv_bfloat162* kp = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+            for (int z = 0; z < 4; z++) {
+                float2 kk = __bfloat1622float2(kp[z]);
+                acc = fmaf(qs[wq][(u * 4 + z) * 2], kk.x, acc);
+                acc = fmaf(qs[wq][(u * 4 + z) * 2 + 1], kk.y, acc);
+            }
+        }
+        acc *= 0.125f;
+        ps[wq][j] = acc;
+        m = fmaxf(m, acc);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < t; j += 32) {
+        float e = __expf(ps[wq][j] - m);
+        ps[wq][j] = e;
+        sum += e;
+    }
+    const float e_new = __expf(s_new - m);
+    sum = warp_sum(sum) + e_new;
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    float2 o = make_float2(e_new * vf.x, e_new * vf.y);
+    for (int j = 0; j < t; j++) {
+        const float p = ps[wq][j];
+        float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)j * 64 + 2 * lane));
+        o.x = fmaf(p, vv.x, o.x);
+        o.y = fmaf(p, vv.y, o.y);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(att + (int64_t)b * E + c) = __floats2bfloat162_rn(o.x * inv, o.y * inv);
+}
+
+// token sources --------------------------------------------------------------------------------------------------
+// cond token s: x[b,:] = cond_emb[cond[b,s]] + pos_emb_cond[s]                      (transformers.py:224)
+__global__ void __launch_bounds__(256)
+cond_tok_kernel(const StepState* __restrict__ stt, const float* __restrict__ cond_emb, const float* __restrict__ pos_cond,
+                int cond_len, int vocab_cond, int E, float* __restrict__ x) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int b = blockIdx.x, s = stt->s;
+    int64_t c = stt->cond ? stt->cond[(int64_t)b * cond_len + s] : 0;
+    c = c < 0 ? 0 : (c >= vocab_cond ? vocab_cond - 1 : c);
+    for (int e = threadIdx.x; e < E; e += 256) x[(int64_t)b * E + e] = cond_emb[c * E + e] + pos_cond[(int64_t)s * E + e];
+}
+// summed code embeddings in bf16: mode 0 -> all D codes of position idx-1 (body input), mode d>=1 -> codes 0..d-1 of
+// position idx (head input, cumsum)                                              (transformers.py:219-225, 250-255)
+__global__ void __launch_bounds__(64)
+code_sum_kernel(const StepState* __restrict__ stt, const float* __restrict__ cb, int HW, int D, int K, int C, int mode,
+                __nv_bfloat16* __restrict__ out) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int b = blockIdx.x;
+    const int pos = mode == 0 ? stt->idx - 1 : stt->idx;
+    const int nd = mode == 0 ? D : mode;
+    for (int c = threadIdx.x; c < C; c += 64) {
+        float a = 0.f;
+        for (int i = 0; i < nd; i++) {
+            int64_t k = stt->codes[((int64_t)b * HW + pos) * D + i];
+            k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+            a += cb[k * C + c];
+        }
+        out[(int64_t)b * C + c] = __float2bfloat16(a);
+    }
+}
+// bookkeeping: which graph just ran decides what advances
+__global__ void advance_kernel(StepState* stt, int ds, int didx, int dstep) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    if (threadIdx.x == 0) { stt->s += ds; stt->idx += didx; stt->step += dstep; }
+}
+__global__ void __launch_bounds__(256) logits_copy_kernel(const StepState* __restrict__ stt, const float* __restrict__ lg, int d,
+                                                          int64_t n) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    if (!stt->logits_out) return;
+    float* dst = stt->logits_out + (int64_t)(stt->step + d) * n;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) dst[i] = lg[i];
+}
+
+__global__ void init_state_kernel(StepState* dst, StepState v) {
+    if (threadIdx.x == 0) *dst = v;
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct FastLayer {
+    CUtensorMap qkv, proj, fc1, fc2;
+};
+
+struct ArFast {
+    rqb200_ar_config cfg;
+    rqb200_ar_weights w;
+    std::vector<rqb200_block_weights> body, head;
+    std::vector<FastLayer> lbody, lhead;
+    CUtensorMap tm_win, tm_whead, tm_cls;
+    // per (workspace, B) state
+    void* ws_base = nullptr;
+    int B = 0;
+    CUtensorMap tx_xn, tx_att, tx_h, tx_s;
+    cudaGraphExec_t g_cond = nullptr, g_code = nullptr, g_head = nullptr;
+    cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
+    bool use_graph = true, use_pdl = true;
+    int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
+};
+
+struct FastWs {
+    StepState* state;
+    float *XB, *XH, *P, *LOGITS;
+    __nv_bfloat16 *XN, *ATT, *Hh, *S;
+    __nv_bfloat16 *kc_body, *vc_body, *kc_head, *vc_head;
+};
+
+static int pick_split(int n_tiles, int nkb, int want) {
+    int s = want > 0 ? want : 148 / n_tiles;
+    if (s < 1) s = 1;
+    if (s > nkb) s = nkb;
+    return s;
+}
+
+static size_t fast_layout(const ArFast& f, int B, void* base, size_t cap, FastWs* ws) {
+    const rqb200_ar_config& c = f.cfg;
+    Arena a(base, cap);
+    const int64_t E = c.embed_dim, HW = (int64_t)c.H * c.W, Tb = c.cond_len + HW;
+    FastWs w;
+    w.state = a.take<StepState>(1);
+    w.XB = a.take<float>(B * E);
+    w.XH = a.take<float>(B * E);
+    int maxs = std::max(std::max(f.split_qkv * 3, f.split_proj), std::max(f.split_fc2, f.split_fc1 * 4));
+    w.P = a.take<float>((int64_t)maxs * B * E);
+    w.LOGITS = a.take<float>((int64_t)B * c.vocab);
+    w.XN = a.take<__nv_bfloat16>(B * E);
+    w.ATT = a.take<__nv_bfloat16>(B * E);
+    w.Hh = a.take<__nv_bfloat16>(B * 4 * E);
+    w.S = a.take<__nv_bfloat16>((int64_t)B * c.code_dim);
+    const int64_t per_body = (int64_t)B * c.n_head * Tb * 64, per_head = (int64_t)B * c.n_head * c.D * 64;
+    w.kc_body = a.take<__nv_bfloat16>(per_body * c.n_body);
+    w.vc_body = a.take<__nv_bfloat16>(per_body * c.n_body);
+    w.kc_head = a.take<__nv_bfloat16>(per_head * c.n_head_layers);
+    w.vc_head = a.take<__nv_bfloat16>(per_head * c.n_head_layers);
+    if (ws) *ws = w;
+    return a.off + 256;
+}
+
+static int gemm(const ArFast& f, const CUtensorMap& tw, const CUtensorMap& tx, int N_out, int K, int B, int splits, int mode,
+                const float* bias, float bias_scale, void* out, float* partial, const float* residual, int64_t ld_res,
+                const int* res_row_ptr, int64_t res_row_stride, cudaStream_t st) {
+    GemmTcParams p = {};
+    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits; p.mode = mode;
+    p.bias = bias; p.bias_scale = bias_scale; p.out = out; p.ld_out = N_out; p.partial = partial;
+    p.residual = residual; p.ld_res = ld_res; p.res_row_ptr = res_row_ptr; p.res_row_stride = res_row_stride;
+    return launch_gemm_tc(tw, tx, p, f.use_pdl, st);
+}
+
+// one transformer stack on the single new token of every batch row; x lives in `x` (fp32), residual additions are
+// deferred into the next ln_reduce.  On return the LAST block's fc2 partials (+ its bias) are still pending.
+static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& blocks, const std::vector<FastLayer>& maps,
+                      FastWs& ws, float* x, bool first_has_pending, const float* pending_bias, const float* pending_extra,
+                      const float* x_src, __nv_bfloat16* kc, __nv_bfloat16* vc, int Tmax, const int* t_ptr, int t_host,
+                      cudaStream_t st) {
+    const rqb200_ar_config& c = f.cfg;
+    const int E = c.embed_dim, B = f.B;
+    const int64_t per = (int64_t)B * c.n_head * Tmax * 64;
+    for (size_t l = 0; l < blocks.size(); l++) {
+        const rqb200_block_weights& bw = blocks[l];
+        // LN1 (+ pending fc2 reduction of the previous block / previous stack)
+        const bool pend = l > 0 || first_has_pending;
+        const float* pb = l > 0 ? blocks[l - 1].b2 : pending_bias;
+        RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl,
+                           (const float*)(l == 0 ? x_src : x), (const float*)(pend ? ws.P : nullptr), pend ? f.split_fc2 : 0,
+                           (const float*)(pend ? pb : nullptr), (const float*)(l == 0 ? pending_extra : nullptr), x,
+                           (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
+        RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+                     nullptr, 0, st));
+        RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
+                           (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
+                           c.n_head, Tmax, t_ptr, t_host));
+        RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+                     nullptr, 0, st));
+        RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)x,
+                           (const float*)ws.P, f.split_proj, (const float*)bw.bproj, (const float*)nullptr, x,
+                           (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
+        if (f.split_fc1 == 1) {
+            RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, 1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr,
+                         0, st));
+        } else {
+            RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+                         nullptr, 0, st));
+            RQB_TRY(launch_pdl(act_reduce_kernel, dim3(148), dim3(256), 0, st, f.use_pdl, (const float*)ws.P, f.split_fc1,
+                               (const float*)bw.b1, ws.Hh, B, 4 * E));
+        }
+        RQB_TRY(gemm(f, maps[l].fc2, f.tx_h, E, 4 * E, B, f.split_fc2, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+                     nullptr, 0, st));
+    }
+    return 0;
+}
+
+static int record_body(ArFast& f, FastWs& ws, bool cond_token, cudaStream_t st) {
+    const rqb200_ar_config& c = f.cfg;
+    const rqb200_ar_weights& w = f.w;
+    const int E = c.embed_dim, B = f.B, HW = c.H * c.W, Tb = c.cond_len + HW;
+    if (cond_token) {
+        RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B), dim3(256), 0, st, f.use_pdl, (const StepState*)ws.state, w.cond_emb,
+                           w.pos_emb_cond, c.cond_len, c.vocab_cond, E, ws.XB));
+    } else {
+        RQB_TRY(launch_pdl(code_sum_kernel, dim3(B), dim3(64), 0, st, f.use_pdl, (const StepState*)ws.state, w.codebook, HW, c.D,
+                           c.codebook_size, c.code_dim, 0, ws.S));
+        // x = W_in (sum_d e_d) + D b_in + pos_emb_hw[idx-1]       (bias counted D times, transformers.py:220,225)
+        RQB_TRY(gemm(f, f.tm_win, f.tx_s, E, c.code_dim, B, 1, GT_F32, w.b_in, (float)c.D, ws.XB, nullptr,
+                     w.pos_emb_hw - E /* row idx-1 */, 0, &ws.state->idx, E, st));
+    }
+    RQB_TRY(fast_stack(f, f.body, f.lbody, ws, ws.XB, false, nullptr, nullptr, ws.XB, ws.kc_body, ws.vc_body, Tb, &ws.state->s,
+                       0, st));
+    RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, f.use_pdl, ws.state, 1, 0, 0));
+    return 0;
+}
+
+static int record_head(ArFast& f, FastWs& ws, cudaStream_t st) {
+    const rqb200_ar_config& c = f.cfg;
+    const rqb200_ar_weights& w = f.w;
+    const int E = c.embed_dim, B = f.B, HW = c.H * c.W, D = c.D, V = c.vocab;
+    for (int d = 0; d < D; d++) {
+        if (d == 0) {
+            // spatial ctx = body x + pending fc2 of the last body block ; token = ctx + pos_emb_d[0]  (transformers.py:259-270)
+            RQB_TRY(fast_stack(f, f.head, f.lhead, ws, ws.XH, true, f.body.back().b2, w.pos_emb_d, ws.XB, ws.kc_head, ws.vc_head,
+                               D, nullptr, 0, st));
+        } else {
+            RQB_TRY(launch_pdl(code_sum_kernel, dim3(B), dim3(64), 0, st, f.use_pdl, (const StepState*)ws.state, w.codebook, HW, D,
+                               c.codebook_size, c.code_dim, d, ws.S));
+            RQB_TRY(gemm(f, f.tm_whead, f.tx_s, E, c.code_dim, B, 1, GT_F32, w.b_head, 1.f, ws.XH, nullptr,
+                         w.pos_emb_d + (int64_t)d * E, 0, nullptr, 0, st));
+            RQB_TRY(fast_stack(f, f.head, f.lhead, ws, ws.XH, false, nullptr, nullptr, ws.XH, ws.kc_head, ws.vc_head, D, nullptr, d,
+                               st));
+        }
+        // classifier: LN(x + pending fc2) -> logits                                              (transformers.py:278-285)
+        RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)ws.XH,
+                           (const float*)ws.P, f.split_fc2, (const float*)f.head.back().b2, (const float*)nullptr,
+                           (float*)nullptr, w.cls_ln_w, w.cls_ln_b, ws.XN, B, E));
+        RQB_TRY(gemm(f, f.tm_cls, f.tx_xn, V, E, B, 1, GT_F32, w.b_cls, 1.f, ws.LOGITS, nullptr, nullptr, 0, nullptr, 0, st));
+        RQB_TRY(launch_pdl(logits_copy_kernel, dim3(64), dim3(256), 0, st, f.use_pdl, (const StepState*)ws.state,
+                           (const float*)ws.LOGITS, d, (int64_t)B * V));
+        RQB_TRY(launch_sample_dyn(ws.LOGITS, ws.state, d, B, V, HW, D, st, f.use_pdl));
+    }
+    RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, f.use_pdl, ws.state, 0, 1, D));
+    return 0;
+}
+
+static int capture(ArFast& f, FastWs& ws, int which, cudaGraphExec_t* out) {
+    cudaGraph_t g = nullptr;
+    if (!f.cap_stream) RQB_CUDA(cudaStreamCreateWithFlags(&f.cap_stream, cudaStreamNonBlocking));
+    cudaStream_t st = f.cap_stream;
+    RQB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = which == 0 ? record_body(f, ws, true, st) : which == 1 ? record_body(f, ws, false, st) : record_head(f, ws, st);
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(RQB200_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(RQB200_ECUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+static void drop_graphs(ArFast& f) {
+    if (f.g_cond) cudaGraphExecDestroy(f.g_cond);
+    if (f.g_code) cudaGraphExecDestroy(f.g_code);
+    if (f.g_head) cudaGraphExecDestroy(f.g_head);
+    f.g_cond = f.g_code = f.g_head = nullptr;
+}
+
+ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, const rqb200_block_weights* body_p,
+                       const rqb200_block_weights* head_p) {
+    std::vector<rqb200_block_weights> body(body_p, body_p + cfg.n_body), head(head_p, head_p + cfg.n_head_layers);
+    const int E = cfg.embed_dim;
+    if (E % 128 != 0 || cfg.vocab % 128 != 0 || cfg.code_dim % 64 != 0 || cfg.D > 8 || cfg.cond_len + cfg.H * cfg.W > AF_MAXT) {
+        set_error("ar fast tier: need E % 128 == 0, V % 128 == 0, code_dim % 64 == 0, D <= 8, cond_len + H*W <= 512");
+        return nullptr;
+    }
+    ArFast* f = new ArFast();
+    f->cfg = cfg; f->w = w; f->body = body; f->head = head;
+    const char* e;
+    if ((e = getenv("RQB200_NO_GRAPH")) && e[0] == '1') f->use_graph = false;
+    if ((e = getenv("RQB200_NO_PDL")) && e[0] == '1') f->use_pdl = false;
+    const int nkbE = E / 64;
+    f->split_qkv = pick_split(3 * E / 128, nkbE, getenv("RQB200_SPLIT_QKV") ? atoi(getenv("RQB200_SPLIT_QKV")) : 0);
+    f->split_proj = pick_split(E / 128, nkbE, getenv("RQB200_SPLIT_PROJ") ? atoi(getenv("RQB200_SPLIT_PROJ")) : 0);
+    f->split_fc1 = pick_split(4 * E / 128, nkbE, getenv("RQB200_SPLIT_FC1") ? atoi(getenv("RQB200_SPLIT_FC1")) : 1);
+    f->split_fc2 = pick_split(E / 128, 4 * nkbE, getenv("RQB200_SPLIT_FC2") ? atoi(getenv("RQB200_SPLIT_FC2")) : 0);
+    auto mk = [&](const std::vector<rqb200_block_weights>& bl, std::vector<FastLayer>& out) -> int {
+        out.resize(bl.size());
+        for (size_t l = 0; l < bl.size(); l++) {
+            RQB_TRY(make_tmap_2d(&out[l].qkv, bl[l].wqkv, 1, E, 3 * E, (uint64_t)E * 2, 64, 128));
+            RQB_TRY(make_tmap_2d(&out[l].proj, bl[l].wproj, 1, E, E, (uint64_t)E * 2, 64, 128));
+            RQB_TRY(make_tmap_2d(&out[l].fc1, bl[l].w1, 1, E, 4 * E, (uint64_t)E * 2, 64, 128));
+            RQB_TRY(make_tmap_2d(&out[l].fc2, bl[l].w2, 1, 4 * E, E, (uint64_t)E * 8, 64, 128));
+        }
+        return 0;
+    };
+    int rc = mk(body, f->lbody);
+    if (!rc) rc = mk(head, f->lhead);
+    if (!rc) rc = make_tmap_2d(&f->tm_win, w.w_in, 1, cfg.code_dim, E, (uint64_t)cfg.code_dim * 2, 64, 128);
+    if (!rc) rc = make_tmap_2d(&f->tm_whead, w.w_head, 1, cfg.code_dim, E, (uint64_t)cfg.code_dim * 2, 64, 128);
+    if (!rc) rc = make_tmap_2d(&f->tm_cls, w.w_cls, 1, E, cfg.vocab, (uint64_t)E * 2, 64, 128);
+    if (rc) { delete f; return nullptr; }
+    return f;
+}
+
+void ar_fast_destroy(ArFast* f) {
+    if (!f) return;
+    drop_graphs(*f);
+    if (f->cap_stream) cudaStreamDestroy(f->cap_stream);
+    delete f;
+}
+
+size_t ar_fast_workspace_bytes(const ArFast* f, int B) { return fast_layout(*f, B, nullptr, 0, nullptr); }
+
+int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B, int start_h, int start_w, float temperature,
+                   const int32_t* top_k, const float* top_p, const float* noise, int64_t noise_stride, float* logits_out,
+                   const int64_t* force, int64_t* out, void* wsp, size_t ws_bytes, cudaStream_t st) {
+    const rqb200_ar_config& c = f->cfg;
+    const int E = c.embed_dim, D = c.D, HW = c.H * c.W, cl = c.cond_len;
+    if (B < 1 || B > 256) return fail(RQB200_EINVAL, "ar fast tier: batch must be in [1,256] per call");
+    if (start_h < 0 || start_w < 0 || start_w >= c.W || start_h > c.H) return fail(RQB200_EINVAL, "ar_sample: bad start_loc");
+    FastWs ws;
+    size_t need = fast_layout(*f, B, wsp, ws_bytes, &ws);
+    if (need > ws_bytes) return fail(RQB200_EWORKSPACE, "ar_sample: workspace too small");
+    if (out != partial)
+        RQB_CUDA(cudaMemcpyAsync(out, partial, (size_t)B * HW * D * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    const int idx0 = start_h * c.W + start_w;
+    if (idx0 >= HW) return 0;
+    if (f->ws_base != wsp || f->B != B) {        // (re)bind activation tensor maps + graphs to this workspace
+        drop_graphs(*f);
+        f->ws_base = wsp;
+        f->B = B;
+        const int bn = gemm_tc_bn(B);
+        RQB_TRY(make_tmap_2d(&f->tx_xn, ws.XN, 1, E, B, (uint64_t)E * 2, 64, bn));
+        RQB_TRY(make_tmap_2d(&f->tx_att, ws.ATT, 1, E, B, (uint64_t)E * 2, 64, bn));
+        RQB_TRY(make_tmap_2d(&f->tx_h, ws.Hh, 1, 4 * E, B, (uint64_t)E * 8, 64, bn));
+        RQB_TRY(make_tmap_2d(&f->tx_s, ws.S, 1, c.code_dim, B, (uint64_t)c.code_dim * 2, 64, bn));
+    }
+    StepState h = {};
+    h.s = 0; h.idx = 0; h.step = 0;
+    h.cond = cond; h.codes = out; h.force = force; h.noise = noise; h.logits_out = logits_out; h.noise_stride = noise_stride;
+    h.temperature = temperature;
+    for (int d = 0; d < D; d++) { h.top_k[d] = top_k[d]; h.top_p[d] = top_p[d]; }
+    RQB_TRY(launch_pdl(init_state_kernel, dim3(1), dim3(32), 0, st, false, ws.state, h));
+    auto run = [&](int which, cudaGraphExec_t* g) -> int {
+        if (!f->use_graph) return which == 0 ? record_body(*f, ws, true, st) : which == 1 ? record_body(*f, ws, false, st)
+                                                                                        : record_head(*f, ws, st);
+        if (!*g) RQB_TRY(capture(*f, ws, which, g));
+        RQB_CUDA(cudaGraphLaunch(*g, st));
+        g_launches++;
+        return 0;
+    };
+    // prefill: cond tokens, then (resume) the code tokens of positions < idx0, one cached step each -- causal, so
+    // identical to the reference's batched prefill (transformers.py:237-239)
+    for (int s = 0; s < cl; s++) RQB_TRY(run(0, &f->g_cond));
+    // state.idx must equal (position whose codes feed the body) + 1 while replaying the code-token graph
+    for (int j = 1; j <= idx0; j++) {
+        RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, false, ws.state, 0, 1, 0));
+        RQB_TRY(run(1, &f->g_code));
+    }
+    for (int idx = idx0; idx < HW; idx++) {
+        if (idx > idx0) RQB_TRY(run(1, &f->g_code));       // body step on the token of position idx-1 (state.idx == idx)
+        RQB_TRY(run(2, &f->g_head));                       // D head steps + sampling; advances idx, step
+    }
+    return 0;
+}
+
+}  // namespace rqb

@@ -149,15 +149,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         tc::mbar_wait(tmem_full, 0);
         tc::tc_fence_after();
         const bool nvalid = n < p.N_out;
-        const float bias = (p.bias != nullptr && nvalid && (p.mode != GT_PARTIAL || split == 0)) ? p.bias[n] : 0.f;
-        int seg = 0, hh = 0, dd = 0, tpos = 0;
-        if (p.mode == GT_QKV) {
-            seg = n / p.E;
-            int e = n % p.E;
-            hh = e >> 6;
-            dd = e & 63;
-            tpos = p.t_ptr ? *p.t_ptr : p.t_host;
-        }
+        const float bias = (p.bias != nullptr && nvalid && p.mode != GT_PARTIAL) ? p.bias[n] * p.bias_scale : 0.f;
+        const float* res = nullptr;
+        if (p.mode == GT_F32 && p.residual != nullptr)
+            res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
             uint32_t r[16];
@@ -171,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 float v = __uint_as_float(r[i]) + bias;
                 switch (p.mode) {
                     case GT_F32:
-                        if (p.residual) v += p.residual[(int64_t)b * p.ld_out + n];
+                        if (res) v += res[(int64_t)b * p.ld_res + n];
                         reinterpret_cast<float*>(p.out)[(int64_t)b * p.ld_out + n] = v;
                         break;
                     case GT_BF16:
@@ -182,13 +177,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         break;
                     case GT_PARTIAL:
                         p.partial[((int64_t)split * p.B + b) * p.N_out + n] = v;
-                        break;
-                    case GT_QKV:
-                        if (seg == 0) p.q_out[(int64_t)b * p.E + hh * 64 + dd] = __float2bfloat16(v);
-                        else {
-                            __nv_bfloat16* c = seg == 1 ? p.kc : p.vc;
-                            c[(((int64_t)b * p.nh + hh) * p.Tmax + tpos) * 64 + dd] = __float2bfloat16(v);
-                        }
                         break;
                 }
             }
@@ -228,11 +216,11 @@ int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcP
     if (p.splits < 1 || p.splits > p.K / 64) return fail(RQB200_EINVAL, "gemm_tc: bad split count");
     const int bn = gemm_tc_bn(p.B);
     switch (bn) {
-        case 16: return launch_gemm_tc_t<16, 6>(tmW, tmX, p, pdl, st);
-        case 32: return launch_gemm_tc_t<32, 5>(tmW, tmX, p, pdl, st);
-        case 64: return launch_gemm_tc_t<64, 4>(tmW, tmX, p, pdl, st);
-        case 128: return launch_gemm_tc_t<128, 3>(tmW, tmX, p, pdl, st);
-        default: return launch_gemm_tc_t<256, 2>(tmW, tmX, p, pdl, st);
+        case 16: return launch_gemm_tc_t<16, 8>(tmW, tmX, p, pdl, st);
+        case 32: return launch_gemm_tc_t<32, 8>(tmW, tmX, p, pdl, st);
+        case 64: return launch_gemm_tc_t<64, 8>(tmW, tmX, p, pdl, st);
+        case 128: return launch_gemm_tc_t<128, 6>(tmW, tmX, p, pdl, st);
+        default: return launch_gemm_tc_t<256, 4>(tmW, tmX, p, pdl, st);
     }
 }
 
@@ -249,7 +237,7 @@ extern "C" int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const 
     RQB_TRY(make_tmap_2d(&tx, X_bf16, 1, (uint64_t)K, (uint64_t)B, (uint64_t)K * 2, 64, (uint32_t)bn));
     GemmTcParams p = {};
     p.N_out = N_out; p.K = K; p.B = B; p.splits = splits;
-    p.bias = bias; p.residual = residual; p.out = out; p.ld_out = N_out; p.partial = partial;
+    p.bias = bias; p.bias_scale = 1.f; p.residual = residual; p.ld_res = N_out; p.out = out; p.ld_out = N_out; p.partial = partial;
     p.mode = splits > 1 ? GT_PARTIAL : (out_is_bf16 ? (gelu ? GT_BF16_GELU : GT_BF16) : GT_F32);
     return launch_gemm_tc(tw, tx, p, false, (cudaStream_t)stream);
 }

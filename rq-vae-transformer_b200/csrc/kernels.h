@@ -49,21 +49,49 @@ int launch_vae_attn(const float* qkv, float* out, int B, int HW, int C, cudaStre
 size_t groupnorm_ws_doubles(int B, int HW);
 
 // gemm_tc.cu -- tcgen05 weight-streaming GEMM (fast tier)
-enum GemmTcMode { GT_F32 = 0, GT_BF16 = 1, GT_BF16_GELU = 2, GT_PARTIAL = 3, GT_QKV = 4 };
+enum GemmTcMode { GT_F32 = 0, GT_BF16 = 1, GT_BF16_GELU = 2, GT_PARTIAL = 3 };
 struct GemmTcParams {
     int N_out, K, B, splits, mode;
-    const float* bias;            // [N_out] (nullable)
-    const float* residual;        // GT_F32 only: out = residual + ...   [B, ld_out]
+    const float* bias;            // [N_out] (nullable); added as bias * bias_scale
+    float bias_scale;
+    // GT_F32 only: out = acc + bias + residual[(row0 * res_row_stride) + b * ld_res + n], row0 = res_row_ptr ? *res_row_ptr : 0
+    // (ld_res = 0 broadcasts one row -- positional embeddings)
+    const float* residual;
+    int64_t ld_res, res_row_stride;
+    const int* res_row_ptr;
     void* out;                    // [B, ld_out] f32 / bf16
     int64_t ld_out;
-    float* partial;               // GT_PARTIAL: [splits][B][N_out] f32
-    // GT_QKV: rows [0,E) -> q_out [B,E] bf16 ; [E,2E) -> kc ; [2E,3E) -> vc  (cache [B][nh][Tmax][64] bf16, row *t_ptr)
-    __nv_bfloat16 *q_out, *kc, *vc;
-    int E, nh, Tmax, t_host;
-    const int* t_ptr;
+    float* partial;               // GT_PARTIAL: [splits][B][N_out] f32 (no bias)
 };
 inline int gemm_tc_bn(int B) { return B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : B <= 128 ? 128 : 256; }
 int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st);
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes_log2, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
+// ar_fast.cu / sampler.cu -- device-resident per-call state of the fast AR tier
+struct StepState {
+    int s;          // body sequence index of the token being processed (= cached body keys before it)
+    int idx;        // spatial position whose codes are being sampled
+    int step;       // tokens sampled so far in this call (indexes noise / logits_out)
+    int pad;
+    const int64_t* cond;      // [B, cond_len] or null
+    int64_t* codes;           // [B, HW, D] working copy (xs)
+    const int64_t* force;     // teacher forcing or null
+    const float* noise;       // [n_tok][B][V] or null
+    float* logits_out;        // [n_tok][B][V] or null
+    int64_t noise_stride;
+    float temperature;
+    int top_k[8];
+    float top_p[8];
+};
+int launch_sample_dyn(const float* logits, const StepState* stt, int d, int B, int V, int HW, int D, cudaStream_t st, bool pdl);
+
+struct ArFast;
+ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, const rqb200_block_weights* body,
+                       const rqb200_block_weights* head);
+void ar_fast_destroy(ArFast* f);
+size_t ar_fast_workspace_bytes(const ArFast* f, int B);
+int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B, int start_h, int start_w, float temperature,
+                   const int32_t* top_k, const float* top_p, const float* noise, int64_t noise_stride, float* logits_out,
+                   const int64_t* force, int64_t* out, void* wsp, size_t ws_bytes, cudaStream_t st);
 }  // namespace rqb

@@ -16,7 +16,8 @@
 //      double accumulator for float), cut after the first position whose cumulative mass >= p, renormalise by the
 //      kept mass.
 //   5. out = argmax_i p_i / q_i, first index on ties.
-#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
 
 namespace rqb {
 
@@ -42,7 +43,8 @@ __device__ __forceinline__ bool item_before(const SortItem& a, const SortItem& b
 
 __global__ void __launch_bounds__(SMP_THREADS, 1)
 sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise, int V, float temperature, int top_k,
-              float top_p, int64_t* __restrict__ out_idx, const int64_t* __restrict__ force, int64_t out_stride) {
+              float top_p, int64_t* __restrict__ out_idx, const int64_t* __restrict__ force, int64_t out_stride,
+              const StepState* __restrict__ stt, int dyn_d, int dyn_HW, int dyn_D) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);                       // [V]   scaled logits, later probabilities
     SortItem* items = reinterpret_cast<SortItem*>(xs + V);                // [Vpad] only touched when top_p < 1
@@ -56,6 +58,18 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise
 
     const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const float* lg = logits + (int64_t)row * V;
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    if (stt != nullptr) {   // fast AR tier: per-token pointers and settings come from the device-resident StepState
+        const int64_t off = (int64_t)stt->idx * dyn_D + dyn_d;
+        out_idx = stt->codes + off;
+        force = stt->force ? stt->force + off : nullptr;
+        out_stride = (int64_t)dyn_HW * dyn_D;
+        qnoise = stt->noise ? stt->noise + (int64_t)(stt->step + dyn_d) * stt->noise_stride : nullptr;
+        temperature = stt->temperature;
+        top_k = stt->top_k[dyn_d];
+        top_p = stt->top_p[dyn_d];
+    }
 
     if (force != nullptr) {   // teacher forcing: emit the forced code, skip the work
         if (t == 0) out_idx[(int64_t)row * out_stride] = force[(int64_t)row * out_stride];
@@ -247,8 +261,35 @@ int launch_sample(const float* logits, const float* q, int B, int V, float tempe
         RQB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMP_MAXV * 12)));
         attr = SMP_MAXV * 12;
     }
-    sample_kernel<<<B, SMP_THREADS, smem, st>>>(logits, q, V, temperature, top_k, top_p, out_idx, force, out_stride);
+    sample_kernel<<<B, SMP_THREADS, smem, st>>>(logits, q, V, temperature, top_k, top_p, out_idx, force, out_stride, nullptr, 0, 0,
+                                                0);
     return check_launch("sample_logits");
+}
+
+int launch_sample_dyn(const float* logits, const StepState* stt, int d, int B, int V, int HW, int D, cudaStream_t st, bool pdl) {
+    if (V <= 0 || V > SMP_MAXV) return fail(RQB200_EINVAL, "sample: V must be in [1,16384]");
+    int vpad = 1;
+    while (vpad < V) vpad <<= 1;
+    size_t smem = (size_t)V * sizeof(float) + (size_t)vpad * sizeof(SortItem);   // top_p is only known on the device
+    static bool attr = false;
+    if (!attr) {
+        RQB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMP_MAXV * 12)));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B);
+    cfg.blockDim = dim3(SMP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RQB_CUDA(cudaLaunchKernelEx(&cfg, sample_kernel, logits, (const float*)nullptr, V, 1.0f, 0, 1.0f, (int64_t*)nullptr,
+                                (const int64_t*)nullptr, (int64_t)0, stt, d, HW, D));
+    g_launches++;
+    return 0;
 }
 
 }  // namespace rqb

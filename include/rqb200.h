@@ -155,6 +155,13 @@ int64_t rqb200_vae_last_launches(const rqb200_vae* h);
 int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out,
                        int out_is_bf16, int gelu, float* partial, int N_out, int K, int B, int splits, void* stream);
 
+/* rqb200_dbg_conv_tc: one launch of the tcgen05 implicit-GEMM conv (csrc/conv_tc.cu): X NHWC fp16 [B,H,W,Cin], W OHWI fp16
+ * [Cout,ks,ks,Cin], stride 1 "same" padding, out f32 NHWC (+bias, +residual) or NCHW when out_nchw.  X16lo / W16lo
+ * (both or neither): the fp16 "lo" halves (value - fp16(value)) -> split-fp16, three products per conv. */
+int rqb200_dbg_conv_tc(const void* X16, const void* W16, const void* X16lo, const void* W16lo, const float* bias,
+                       const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ks, int out_nchw,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,6 +199,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     }
 }
 
+int launch_gn_stats(const float* X, double* stats_ws, int B, int HW, int C, cudaStream_t st) {
+    if (C % GN_G != 0) return fail(RQB200_EINVAL, "groupnorm: C % 32 != 0");
+    gn_stats_kernel<<<dim3((unsigned)ceil_div(HW, GN_PIX), B), 256, 0, st>>>(X, stats_ws, HW, C);
+    return check_launch("gn_stats");
+}
+
 int launch_groupnorm_silu(const float* X, const float* gamma, const float* beta, float* Y, double* stats_ws, int B, int HW,
                           int C, int silu, cudaStream_t st) {
     if (C % GN_G != 0) return fail(RQB200_EINVAL, "groupnorm: C % 32 != 0");

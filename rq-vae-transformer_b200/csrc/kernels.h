@@ -47,6 +47,17 @@ int launch_groupnorm_silu(const float* X, const float* gamma, const float* beta,
                           int C, int silu, cudaStream_t st);
 int launch_vae_attn(const float* qkv, float* out, int B, int HW, int C, cudaStream_t st);
 size_t groupnorm_ws_doubles(int B, int HW);
+int launch_gn_stats(const float* X, double* stats_ws, int B, int HW, int C, cudaStream_t st);
+// conv_tc.cu -- tcgen05 implicit-GEMM conv (fast tier) and its fp16 operand producers
+bool conv_tc_supported(int H, int W, int Cin, int Cout, int ks, int stride, int in_nchw);
+int launch_conv_tc(const void* X16, const void* W16, const void* X16lo, const void* W16lo, const float* bias,
+                   const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ks, int out_nchw,
+                   cudaStream_t st);
+int launch_groupnorm_f16(const float* X, const float* gamma, const float* beta, void* Y16, void* Y16lo, double* stats_ws, int B,
+                         int HW, int C, int silu, cudaStream_t st);
+int launch_cast_f16(const float* X, void* Y16, void* Y16lo, int B, int H, int W, int C, int upsample, cudaStream_t st);
+int make_tmap_4d_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_c,
+                      uint32_t box_w, uint32_t box_h, uint32_t box_b);
 
 // gemm_tc.cu -- tcgen05 weight-streaming GEMM (fast tier)
 enum GemmTcMode { GT_F32 = 0, GT_BF16 = 1, GT_BF16_GELU = 2, GT_PARTIAL = 3 };

@@ -22,6 +22,8 @@ struct rqb200_vae {
     rqb200_vae_config cfg;
     std::unordered_map<std::string, VTensor> t;
     bool finalized = false;
+    bool fast_ok = false;     // FAST mode and every decoder channel count is a multiple of 128
+    bool split = false;       // split-fp16 (3 products per conv): "<key>.weight_lo" tensors registered
     int64_t last_launches = 0;
     int64_t max_act = 0;      // max H*W*C per image over all activations
     int64_t max_gn_hw = 0;
@@ -37,6 +39,94 @@ struct VaeRun {
     float* buf[4];
     double* gn_ws;
     std::string missing;
+    __half* h16[2] = {nullptr, nullptr};      // fast tier: fp16 conv operands (GN output / cast / upsampled cast)
+    __half* l16[2] = {nullptr, nullptr};      // their fp16 'lo' halves (split-fp16 products); null -> single product
+    bool fast = false;
+
+    // ---- fast tier helpers (tcgen05 implicit GEMM; decoder only, C % 128 == 0 everywhere)
+    int conv_f(const std::string& name, const __half* in16, float* out, const float* resid, int Hh, int Ww, int Cin, int Cout,
+               int ks, int out_nchw) {
+        const VTensor* w = get(name + ".weight", (int64_t)Cout * ks * ks * Cin);
+        const VTensor* b = get(name + ".bias", Cout);
+        note_act((int64_t)Hh * Ww, Cout);
+        if (dry || !w || !b) return 0;
+        if (w->dtype != RQB200_F16) return fail(RQB200_ESTATE, "vae fast tier: conv weights must be fp16: " + name);
+        const __half* in_lo = nullptr;
+        const void* w_lo = nullptr;
+        if (h->split) {
+            const VTensor* wl = get(name + ".weight_lo", (int64_t)Cout * ks * ks * Cin);
+            if (!wl) return 0;
+            w_lo = wl->ptr;
+            in_lo = in16 == h16[0] ? l16[0] : l16[1];
+        }
+        return launch_conv_tc(in16, w->ptr, in_lo, w_lo, (const float*)b->ptr, resid, out, B, Hh, Ww, Cin, Cout, ks, out_nchw, st);
+    }
+    int gn_f(const std::string& name, const float* in, __half* out16, int HW, int C, int silu) {
+        const VTensor* g = get(name + ".weight", C);
+        const VTensor* b = get(name + ".bias", C);
+        if (HW > h->max_gn_hw) h->max_gn_hw = HW;
+        if (dry || !g || !b) return 0;
+        return launch_groupnorm_f16(in, (const float*)g->ptr, (const float*)b->ptr, out16, out16 == h16[0] ? l16[0] : l16[1], gn_ws, B, HW, C, silu, st);
+    }
+    int resblock_f(const std::string& p, int cur, int Hh, int Ww, int Cin, int Cout, int* rc) {
+        int a = (cur + 1) & 3, b = (cur + 2) & 3, c = (cur + 3) & 3;
+        (void)a;
+        *rc = gn_f(p + ".norm1", buf[cur], h16[0], Hh * Ww, Cin, 1); if (*rc) return cur;
+        *rc = conv_f(p + ".conv1", h16[0], buf[b], nullptr, Hh, Ww, Cin, Cout, 3, 0); if (*rc) return cur;
+        *rc = gn_f(p + ".norm2", buf[b], h16[0], Hh * Ww, Cout, 1); if (*rc) return cur;
+        const float* res = buf[cur];
+        if (Cin != Cout) {
+            if (!dry) { *rc = launch_cast_f16(buf[cur], h16[1], l16[1], B, Hh, Ww, Cin, 0, st); if (*rc) return cur; }
+            *rc = conv_f(p + ".nin_shortcut", h16[1], buf[c], nullptr, Hh, Ww, Cin, Cout, 1, 0); if (*rc) return cur;
+            res = buf[c];
+        }
+        *rc = conv_f(p + ".conv2", h16[0], buf[b], res, Hh, Ww, Cout, Cout, 3, 0);
+        return b;
+    }
+    int attnblock_f(const std::string& p, int cur, int Hh, int Ww, int C, int* rc) {
+        int a = (cur + 1) & 3, b = (cur + 2) & 3, c = (cur + 3) & 3;
+        *rc = gn_f(p + ".norm", buf[cur], h16[0], Hh * Ww, C, 0); if (*rc) return cur;
+        *rc = conv_f(p + ".qkv", h16[0], buf[b], nullptr, Hh, Ww, C, 3 * C, 1, 0); if (*rc) return cur;
+        if (!dry && missing.empty()) {
+            *rc = launch_vae_attn(buf[b], buf[a], B, Hh * Ww, C, st); if (*rc) return cur;
+            *rc = launch_cast_f16(buf[a], h16[0], l16[0], B, Hh, Ww, C, 0, st); if (*rc) return cur;
+        }
+        *rc = conv_f(p + ".proj_out", h16[0], buf[c], buf[cur], Hh, Ww, C, C, 1, 0);
+        return c;
+    }
+    int decode_fast(const float* z, float* out) {
+        const rqb200_vae_config& c = h->cfg;
+        const int nl = c.n_levels, nb = c.num_res_blocks;
+        int res = c.resolution >> (nl - 1), rc = 0;
+        int ch = c.ch * c.ch_mult[nl - 1];
+        int cur = 0;
+        if (!dry) { rc = launch_cast_f16(z, h16[0], l16[0], B, res, res, c.embed_dim, 0, st); if (rc) return rc; }
+        rc = conv_f("post_quant_conv", h16[0], buf[1], nullptr, res, res, c.embed_dim, c.z_channels, 1, 0); if (rc) return rc;
+        if (!dry) { rc = launch_cast_f16(buf[1], h16[0], l16[0], B, res, res, c.z_channels, 0, st); if (rc) return rc; }
+        rc = conv_f("decoder.conv_in", h16[0], buf[0], nullptr, res, res, c.z_channels, ch, 3, 0); if (rc) return rc;
+        cur = resblock_f("decoder.mid.block_1", cur, res, res, ch, ch, &rc); if (rc) return rc;
+        cur = attnblock_f("decoder.mid.attn_1", cur, res, res, ch, &rc); if (rc) return rc;
+        cur = resblock_f("decoder.mid.block_2", cur, res, res, ch, ch, &rc); if (rc) return rc;
+        for (int lvl = nl - 1; lvl >= 0; lvl--) {
+            int cout = c.ch * c.ch_mult[lvl];
+            for (int b = 0; b <= nb; b++) {
+                std::string p = "decoder.up." + std::to_string(lvl);
+                cur = resblock_f(p + ".block." + std::to_string(b), cur, res, res, ch, cout, &rc); if (rc) return rc;
+                ch = cout;
+                if (has_attn(res)) { cur = attnblock_f(p + ".attn." + std::to_string(b), cur, res, res, ch, &rc); if (rc) return rc; }
+            }
+            if (lvl != 0) {
+                int nxt = (cur + 1) & 3;
+                if (!dry) { rc = launch_cast_f16(buf[cur], h16[1], l16[1], B, res, res, ch, 1, st); if (rc) return rc; }   // x2 nearest, fp16
+                rc = conv_f("decoder.up." + std::to_string(lvl) + ".upsample.conv", h16[1], buf[nxt], nullptr, 2 * res, 2 * res, ch, ch, 3, 0);
+                if (rc) return rc;
+                cur = nxt;
+                res *= 2;
+            }
+        }
+        rc = gn_f("decoder.norm_out", buf[cur], h16[0], res * res, ch, 1); if (rc) return rc;
+        return conv_f("decoder.conv_out", h16[0], out, nullptr, res, res, ch, c.out_ch, 3, 1);
+    }
 
     const VTensor* get(const std::string& k, int64_t numel) {
         auto it = h->t.find(k);
@@ -101,6 +191,7 @@ struct VaeRun {
 
     // Decoder.forward (modules.py:171-202) preceded by post_quant_conv (rqvae.py:87).  z NHWC [B,r,r,embed_dim].
     int decode(const float* z, float* out) {
+        if (fast) return decode_fast(z, out);
         const rqb200_vae_config& c = h->cfg;
         const int nl = c.n_levels, nb = c.num_res_blocks;
         int res = c.resolution >> (nl - 1), rc = 0;
@@ -174,7 +265,16 @@ static size_t vae_layout(const rqb200_vae* h, int B, void* base, size_t cap, Vae
     const rqb200_vae_config& c = h->cfg;
     int r = c.resolution >> (c.n_levels - 1);
     float* zq = a.take<float>((size_t)B * r * r * c.embed_dim);      // decode_code staging
-    if (run) run->buf[0] = run->buf[0], (void)zq;
+    (void)zq;
+    for (int i = 0; i < 2; i++) {
+        __half* p16 = a.take<__half>((size_t)B * h->max_act);
+        if (run) run->h16[i] = p16;
+    }
+    if (h->split)
+        for (int i = 0; i < 2; i++) {
+            __half* p16 = a.take<__half>((size_t)B * h->max_act);
+            if (run) run->l16[i] = p16;
+        }
     return a.off + 256;
 }
 
@@ -211,7 +311,17 @@ int rqb200_vae_finalize(rqb200_vae* h) {
     rqb::VaeRun run{h, nullptr, 1, true, {nullptr, nullptr, nullptr, nullptr}, nullptr, ""};
     h->max_act = 0;
     h->max_gn_hw = 0;
+    {
+        const rqb200_vae_config& c = h->cfg;
+        int r = c.resolution >> (c.n_levels - 1);
+        bool ok = c.mode == RQB200_MODE_FAST && c.ch % 128 == 0 && c.z_channels % 128 == 0 && c.embed_dim % 128 == 0 &&
+                  c.out_ch == 3 && r > 0 && (r & (r - 1)) == 0;
+        h->fast_ok = ok;
+        h->split = ok && h->t.find("decoder.conv_in.weight_lo") != h->t.end();
+    }
+    run.fast = h->fast_ok;
     run.decode(nullptr, nullptr);
+    run.fast = false;
     run.encode(nullptr, nullptr);
     if (!run.missing.empty()) return rqb::fail(RQB200_ESTATE, "vae_finalize: tensor " + run.missing);
     if (h->t.find("codebook") == h->t.end()) return rqb::fail(RQB200_ESTATE, "vae_finalize: tensor codebook (missing)");
@@ -230,6 +340,7 @@ static int vae_prepare(rqb200_vae* h, int B, void* ws, size_t ws_bytes, void* st
     if (B <= 0) return rqb::fail(RQB200_EINVAL, "vae: B must be > 0");
     if (rqb200_device_count() <= 0) return rqb::fail(RQB200_ENODEV, "vae: no CUDA device");
     *run = rqb::VaeRun{h, (cudaStream_t)stream, B, false, {nullptr, nullptr, nullptr, nullptr}, nullptr, ""};
+    run->fast = h->fast_ok;
     size_t need = rqb::vae_layout(h, B, ws, ws_bytes, run);
     if (need > ws_bytes) return rqb::fail(RQB200_EWORKSPACE, "vae: workspace too small");
     rqb::g_launches = 0;
@@ -264,6 +375,7 @@ int rqb200_vae_encode(rqb200_vae* h, const float* x, int B, float* z_e, void* wo
                       void* stream) {
     rqb::VaeRun run;
     RQB_TRY(vae_prepare(h, B, workspace, workspace_bytes, stream, &run));
+    run.fast = false;            // encoder: exact-tier kernels (stride-2 convs / Cin=3 are not on the tcgen05 path yet)
     int rc = run.encode(x, z_e);
     h->last_launches = rqb::g_launches;
     return rc;

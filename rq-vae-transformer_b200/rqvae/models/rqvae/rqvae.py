@@ -36,6 +36,7 @@ class RQVAE(Stage1Model):
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.loss_type, self.latent_loss_weight = loss_type, latent_loss_weight
         self.precision = None            # None -> _native.default_precision() ('auto' == exact until told otherwise)
+        self.split_fp16 = True           # fast tier: 3-product split-fp16 convs (keeps 60 chained convs within 1e-3)
         self._eng = {}                   # (device, mode) -> dict(handle, tensors, ws)
         self.last_launches = 0
 
@@ -65,7 +66,7 @@ class RQVAE(Stage1Model):
 
     def _engine(self, device):
         mode = self._mode()
-        key = (str(device), mode)
+        key = (str(device), mode, self.split_fp16)
         if key in self._eng:
             return self._eng[key]
         L = N.lib()
@@ -91,6 +92,17 @@ class RQVAE(Stage1Model):
             keep[name] = t
             N.check(L.rqb200_vae_set_tensor(handle, name.encode(), N.ptr(t), N.dtype_code(t), t.numel()), "vae_set_tensor")
 
+        def reg_conv(name, w_oihw):
+            """conv weight OIHW -> OHWI in the engine's dtype; fast tier: fp16 hi + lo halves (split-fp16 products)"""
+            w = w_oihw.detach().permute(0, 2, 3, 1).contiguous().float()
+            if mode == N.MODE_FAST and name.startswith(("decoder.", "post_quant_conv")):
+                hi = w.to(torch.float16)
+                reg(name, hi)
+                if self.split_fp16:
+                    reg(name + "_lo", (w - hi.float()).to(torch.float16))
+            else:
+                reg(name, w)          # exact tier, and the encoder in every tier (fp32 FFMA kernels)
+
         sd = {k: v for k, v in self.state_dict().items()}
         for k, v in sd.items():
             if not (k.startswith("encoder.") or k.startswith("decoder.") or k.startswith("quant_conv") or
@@ -100,7 +112,7 @@ class RQVAE(Stage1Model):
             if v.dim() == 4:                                   # conv weight OIHW -> OHWI in the engine's weight dtype
                 if k.endswith((".q.weight", ".k.weight", ".v.weight")):
                     continue
-                reg(k, v.permute(0, 2, 3, 1).to(wdt))
+                reg_conv(k, v)
             elif k.endswith((".q.bias", ".k.bias", ".v.bias")):
                 continue
             else:
@@ -109,7 +121,7 @@ class RQVAE(Stage1Model):
             base = k[:-len(".q.weight")]
             w = torch.cat([sd[base + ".q.weight"], sd[base + ".k.weight"], sd[base + ".v.weight"]], 0)
             b = torch.cat([sd[base + ".q.bias"], sd[base + ".k.bias"], sd[base + ".v.bias"]], 0)
-            reg(base + ".qkv.weight", w.permute(0, 2, 3, 1).to(wdt))
+            reg_conv(base + ".qkv.weight", w)
             reg(base + ".qkv.bias", b.float())
         reg("codebook", self.quantizer._shared_table().float())
         N.check(L.rqb200_vae_finalize(handle), "vae_finalize")

@@ -6,6 +6,8 @@ from rqvae import _native as N
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def gelu(x):
@@ -40,3 +42,35 @@ def test_gemm_tc_matches_fp32_matmul(N_out, K, B, splits):
         N.check(L.rqb200_dbg_gemm_tc(N.ptr(W), N.ptr(X), None, None, None, 0, 0, N.ptr(part), N_out, K, B, splits, st))
         torch.cuda.synchronize()
         torch.testing.assert_close(part.sum(0), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ks,nchw,res", [
+    (2, 8, 8, 256, 512, 3, 0, 0), (3, 16, 16, 512, 512, 1, 0, 1), (1, 64, 64, 256, 256, 3, 0, 1),
+    (2, 256, 256, 128, 128, 3, 0, 1), (2, 256, 256, 128, 3, 3, 1, 0), (5, 8, 8, 512, 1536, 1, 0, 0),
+    (1, 32, 32, 512, 256, 3, 0, 0), (2, 128, 128, 256, 128, 1, 0, 0)])
+@pytest.mark.parametrize("split", [0, 1])
+def test_conv_tc_matches_fp32_conv(B, H, W, Cin, Cout, ks, nchw, res, split):
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, ks, ks, generator=g) / (Cin * ks * ks) ** 0.5
+    if not split:                       # single product: operands ARE fp16 values
+        x, w = x.to(torch.float16).float(), w.to(torch.float16).float()
+    bias = torch.randn(Cout, generator=g)
+    R = torch.randn(B, Cout, H, W, generator=g)
+    ref = torch.nn.functional.conv2d(x.double().to(DEV), w.double().to(DEV), bias.double().to(DEV), padding=ks // 2).float()
+    if res:
+        ref = ref + R.to(DEV)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    w_ohwi = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    x_hi, w_hi = x_nhwc.half(), w_ohwi.half()
+    x_lo = (x_nhwc - x_hi.float()).half() if split else None
+    w_lo = (w_ohwi - w_hi.float()).half() if split else None
+    r_nhwc = R.permute(0, 2, 3, 1).contiguous().to(DEV) if res else None
+    out = torch.full((B, Cout, H, W) if nchw else (B, H, W, Cout), float("nan"), device=DEV)
+    L = N.lib()
+    N.check(L.rqb200_dbg_conv_tc(N.ptr(x_hi), N.ptr(w_hi), N.ptr(x_lo), N.ptr(w_lo), N.ptr(bias.to(DEV)), N.ptr(r_nhwc), N.ptr(out),
+                                 B, H, W, Cin, Cout, ks, nchw, N.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out if nchw else out.permute(0, 3, 1, 2)
+    # fp32 accumulate of exact fp16 products (split: of fp32-class products): summation order only
+    torch.testing.assert_close(got, ref, rtol=1e-4 if split else 2e-3, atol=1e-4 if split else 2e-3)

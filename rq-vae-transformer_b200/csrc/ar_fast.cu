@@ -251,10 +251,18 @@ struct ArFast {
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
     bool use_graph = true, use_pdl = true;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
+    // persistent ("mega") form: phase programs living in the workspace
+    bool want_mega = false, use_mega = false;   // opt-in (RQB200_MEGA=1): measured slower than the PDL chain so far, see DESIGN.md
+    int mega_split_fc1 = 3;
+    int n_sm = 148;
+    MegaParams prog_cond = {}, prog_code = {}, prog_head[8] = {};
 };
 
 struct FastWs {
     StepState* state;
+    MPhase* tables;
+    unsigned* bar;
+    long long* trace;
     float *XB, *XH, *P, *LOGITS;
     __nv_bfloat16 *XN, *ATT, *Hh, *S;
     __nv_bfloat16 *kc_body, *vc_body, *kc_head, *vc_head;
@@ -273,9 +281,12 @@ static size_t fast_layout(const ArFast& f, int B, void* base, size_t cap, FastWs
     const int64_t E = c.embed_dim, HW = (int64_t)c.H * c.W, Tb = c.cond_len + HW;
     FastWs w;
     w.state = a.take<StepState>(1);
+    w.bar = a.take<unsigned>(64);
+    w.trace = a.take<long long>(4096);
+    w.tables = a.take<MPhase>((size_t)(8 * c.n_body) * 2 + 2 + (size_t)c.D * (4 + 8 * c.n_head_layers) + 8);
     w.XB = a.take<float>(B * E);
     w.XH = a.take<float>(B * E);
-    int maxs = std::max(std::max(f.split_qkv * 3, f.split_proj), std::max(f.split_fc2, f.split_fc1 * 4));
+    int maxs = std::max(std::max(f.split_qkv * 3, f.split_proj), std::max(f.split_fc2, std::max(f.split_fc1, f.mega_split_fc1) * 4));
     w.P = a.take<float>((int64_t)maxs * B * E);
     w.LOGITS = a.take<float>((int64_t)B * c.vocab);
     w.XN = a.take<__nv_bfloat16>(B * E);
@@ -344,10 +355,115 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
     return 0;
 }
 
+// ---- persistent form: the same chains as fast_stack/record_*, expressed as phase tables for ar_mega_kernel
+static int build_programs(ArFast& f, FastWs& ws) {
+    const rqb200_ar_config& c = f.cfg;
+    const rqb200_ar_weights& w = f.w;
+    const int E = c.embed_dim, B = f.B, HW = c.H * c.W, Tb = c.cond_len + HW, D = c.D, V = c.vocab;
+    CUtensorMap mx_xn, mx_att, mx_h, mx_s;
+    RQB_TRY(make_tmap_2d(&mx_xn, ws.XN, 1, E, B, (uint64_t)E * 2, 64, 64));
+    RQB_TRY(make_tmap_2d(&mx_att, ws.ATT, 1, E, B, (uint64_t)E * 2, 64, 64));
+    RQB_TRY(make_tmap_2d(&mx_h, ws.Hh, 1, 4 * E, B, (uint64_t)E * 8, 64, 64));
+    RQB_TRY(make_tmap_2d(&mx_s, ws.S, 1, c.code_dim, B, (uint64_t)c.code_dim * 2, 64, 64));
+    std::vector<MPhase> all;
+    auto ln = [&](const float* x_in, bool pend, int S, const float* bias, const float* extra, float* x_out, const float* g,
+                  const float* be, __nv_bfloat16* xn) {
+        MPhase p = {};
+        p.type = MP_LN; p.x_in = x_in; p.partial = pend ? ws.P : nullptr; p.S = pend ? S : 0; p.bias = pend ? bias : nullptr;
+        p.extra = extra; p.x_out = x_out; p.g = g; p.be = be; p.xn = xn;
+        all.push_back(p);
+    };
+    auto gm = [&](const CUtensorMap& tw, const CUtensorMap& tx, int N_out, int K, int splits, int mode, const float* bias,
+                  float bias_scale, void* out, const float* res, int64_t ld_res, const int* res_row_ptr, int64_t res_row_stride) {
+        MPhase p = {};
+        p.type = MP_GEMM; p.tmW = tw; p.tmX = tx; p.N_out = N_out; p.K = K; p.splits = splits; p.mode = mode; p.gbias = bias;
+        p.bias_scale = bias_scale; p.out = out; p.gpartial = ws.P; p.res = res; p.ld_res = ld_res; p.res_row_ptr = res_row_ptr;
+        p.res_row_stride = res_row_stride;
+        all.push_back(p);
+    };
+    auto stack = [&](const std::vector<rqb200_block_weights>& blocks, const std::vector<FastLayer>& maps, float* x, bool first_pending,
+                     const float* pending_bias, const float* pending_extra, const float* x_src, __nv_bfloat16* kc,
+                     __nv_bfloat16* vc, int Tmax, const int* t_ptr, int t_host) {
+        const int64_t per = (int64_t)B * c.n_head * Tmax * 64;
+        for (size_t l = 0; l < blocks.size(); l++) {
+            const rqb200_block_weights& bw = blocks[l];
+            const bool pend = l > 0 || first_pending;
+            ln(l == 0 ? x_src : x, pend, f.split_fc2, l > 0 ? blocks[l - 1].b2 : pending_bias, l == 0 ? pending_extra : nullptr, x,
+               bw.ln1_w, bw.ln1_b, ws.XN);
+            gm(maps[l].qkv, mx_xn, 3 * E, E, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, nullptr, 0, nullptr, 0);
+            MPhase a = {};
+            a.type = MP_ATTN; a.apart = ws.P; a.aS = f.split_qkv; a.bqkv = bw.bqkv; a.kc = kc + per * l; a.vc = vc + per * l;
+            a.att = ws.ATT; a.Tmax = Tmax; a.t_ptr = t_ptr; a.t_host = t_host;
+            all.push_back(a);
+            gm(maps[l].proj, mx_att, E, E, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, nullptr, 0, nullptr, 0);
+            ln(x, true, f.split_proj, bw.bproj, nullptr, x, bw.ln2_w, bw.ln2_b, ws.XN);
+            if (f.mega_split_fc1 <= 1) {
+                gm(maps[l].fc1, mx_xn, 4 * E, E, 1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr, 0, nullptr, 0);
+            } else {
+                gm(maps[l].fc1, mx_xn, 4 * E, E, f.mega_split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, nullptr, 0, nullptr, 0);
+                MPhase a2 = {};
+                a2.type = MP_ACT; a2.N_out = 4 * E; a2.splits = f.mega_split_fc1; a2.gbias = bw.b1; a2.gpartial = ws.P; a2.out = ws.Hh;
+                all.push_back(a2);
+            }
+            gm(maps[l].fc2, mx_h, E, 4 * E, f.split_fc2, GT_PARTIAL, nullptr, 1.f, nullptr, nullptr, 0, nullptr, 0);
+        }
+    };
+    auto cs = [&](int mode) {
+        MPhase p = {};
+        p.type = MP_CODESUM; p.cs_mode = mode; p.cs_out = ws.S;
+        all.push_back(p);
+    };
+    std::vector<std::pair<size_t, size_t>> spans;      // [begin, end) per program: cond, code, head 0..D-1
+    size_t b0 = all.size();
+    stack(f.body, f.lbody, ws.XB, false, nullptr, nullptr, ws.XB, ws.kc_body, ws.vc_body, Tb, &ws.state->s, 0);
+    spans.push_back({b0, all.size()});
+    b0 = all.size();
+    cs(0);
+    gm(f.tm_win, mx_s, E, c.code_dim, 1, GT_F32, w.b_in, (float)D, ws.XB, w.pos_emb_hw - E, 0, &ws.state->idx, E);
+    stack(f.body, f.lbody, ws.XB, false, nullptr, nullptr, ws.XB, ws.kc_body, ws.vc_body, Tb, &ws.state->s, 0);
+    spans.push_back({b0, all.size()});
+    for (int d = 0; d < D; d++) {
+        b0 = all.size();
+        if (d == 0) {
+            stack(f.head, f.lhead, ws.XH, true, f.body.back().b2, w.pos_emb_d, ws.XB, ws.kc_head, ws.vc_head, D, nullptr, 0);
+        } else {
+            cs(d);
+            gm(f.tm_whead, mx_s, E, c.code_dim, 1, GT_F32, w.b_head, 1.f, ws.XH, w.pos_emb_d + (int64_t)d * E, 0, nullptr, 0);
+            stack(f.head, f.lhead, ws.XH, false, nullptr, nullptr, ws.XH, ws.kc_head, ws.vc_head, D, nullptr, d);
+        }
+        ln(ws.XH, true, f.split_fc2, f.head.back().b2, nullptr, nullptr, w.cls_ln_w, w.cls_ln_b, ws.XN);
+        gm(f.tm_cls, mx_xn, V, E, 1, GT_F32, w.b_cls, 1.f, ws.LOGITS, nullptr, 0, nullptr, 0);
+        spans.push_back({b0, all.size()});
+    }
+    // one synchronous upload per (workspace, batch) binding
+    RQB_CUDA(cudaMemcpy(ws.tables, all.data(), all.size() * sizeof(MPhase), cudaMemcpyHostToDevice));
+    RQB_CUDA(cudaMemset(ws.bar, 0, 64 * sizeof(unsigned)));
+    auto mk = [&](std::pair<size_t, size_t> sp) {
+        MegaParams P = {};
+        P.phases = ws.tables + sp.first; P.n_phases = (int)(sp.second - sp.first);
+        P.B = B; P.E = E; P.nh = c.n_head; P.bar = ws.bar; P.stt = ws.state;
+        P.codebook = w.codebook; P.HW = HW; P.D = D; P.Kc = c.codebook_size; P.C = c.code_dim;
+        P.trace = (getenv("RQB200_MEGA_TRACE") && P.n_phases < 2000) ? ws.trace : nullptr;
+        return P;
+    };
+    f.prog_cond = mk(spans[0]);
+    f.prog_code = mk(spans[1]);
+    for (int d = 0; d < D; d++) f.prog_head[d] = mk(spans[2 + d]);
+    return 0;
+}
+
 static int record_body(ArFast& f, FastWs& ws, bool cond_token, cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
     const rqb200_ar_weights& w = f.w;
     const int E = c.embed_dim, B = f.B, HW = c.H * c.W, Tb = c.cond_len + HW;
+    if (f.use_mega) {
+        if (cond_token)
+            RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B), dim3(256), 0, st, false, (const StepState*)ws.state, w.cond_emb,
+                               w.pos_emb_cond, c.cond_len, c.vocab_cond, E, ws.XB));
+        RQB_TRY(launch_ar_mega(cond_token ? f.prog_cond : f.prog_code, f.n_sm, st));
+        RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, false, ws.state, 1, 0, 0));
+        return 0;
+    }
     if (cond_token) {
         RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B), dim3(256), 0, st, f.use_pdl, (const StepState*)ws.state, w.cond_emb,
                            w.pos_emb_cond, c.cond_len, c.vocab_cond, E, ws.XB));
@@ -368,6 +484,16 @@ static int record_head(ArFast& f, FastWs& ws, cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
     const rqb200_ar_weights& w = f.w;
     const int E = c.embed_dim, B = f.B, HW = c.H * c.W, D = c.D, V = c.vocab;
+    if (f.use_mega) {
+        for (int d = 0; d < D; d++) {
+            RQB_TRY(launch_ar_mega(f.prog_head[d], f.n_sm, st));
+            RQB_TRY(launch_pdl(logits_copy_kernel, dim3(64), dim3(256), 0, st, false, (const StepState*)ws.state,
+                               (const float*)ws.LOGITS, d, (int64_t)B * V));
+            RQB_TRY(launch_sample_dyn(ws.LOGITS, ws.state, d, B, V, HW, D, st, false));
+        }
+        RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, false, ws.state, 0, 1, D));
+        return 0;
+    }
     for (int d = 0; d < D; d++) {
         if (d == 0) {
             // spatial ctx = body x + pending fc2 of the last body block ; token = ctx + pos_emb_d[0]  (transformers.py:259-270)
@@ -429,6 +555,14 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     const char* e;
     if ((e = getenv("RQB200_NO_GRAPH")) && e[0] == '1') f->use_graph = false;
     if ((e = getenv("RQB200_NO_PDL")) && e[0] == '1') f->use_pdl = false;
+    if ((e = getenv("RQB200_MEGA")) && e[0] == '1') f->want_mega = true;
+    if ((e = getenv("RQB200_MEGA_SPLIT_FC1"))) f->mega_split_fc1 = atoi(e);
+    f->mega_split_fc1 = pick_split(4 * E / 128, E / 64, f->mega_split_fc1);
+    {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) f->n_sm = n;
+    }
     const int nkbE = E / 64;
     f->split_qkv = pick_split(3 * E / 128, nkbE, getenv("RQB200_SPLIT_QKV") ? atoi(getenv("RQB200_SPLIT_QKV")) : 0);
     f->split_proj = pick_split(E / 128, nkbE, getenv("RQB200_SPLIT_PROJ") ? atoi(getenv("RQB200_SPLIT_PROJ")) : 0);
@@ -485,6 +619,8 @@ int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B
         RQB_TRY(make_tmap_2d(&f->tx_att, ws.ATT, 1, E, B, (uint64_t)E * 2, 64, bn));
         RQB_TRY(make_tmap_2d(&f->tx_h, ws.Hh, 1, 4 * E, B, (uint64_t)E * 8, 64, bn));
         RQB_TRY(make_tmap_2d(&f->tx_s, ws.S, 1, c.code_dim, B, (uint64_t)c.code_dim * 2, 64, bn));
+        f->use_mega = f->want_mega && B <= 64 && E <= 224 * 4 * 3 && mega_smem_bytes(E) <= 227 * 1024;
+        if (f->use_mega) RQB_TRY(build_programs(*f, ws));
     }
     StepState h = {};
     h.s = 0; h.idx = 0; h.step = 0;
@@ -511,6 +647,28 @@ int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B
     for (int idx = idx0; idx < HW; idx++) {
         if (idx > idx0) RQB_TRY(run(1, &f->g_code));       // body step on the token of position idx-1 (state.idx == idx)
         RQB_TRY(run(2, &f->g_head));                       // D head steps + sampling; advances idx, step
+    }
+    if (f->use_mega && getenv("RQB200_MEGA_TRACE")) {      // diagnostics: per-phase time of the LAST launch that wrote the trace
+        cudaStreamSynchronize(st);
+        std::vector<long long> tr(4096);
+        std::vector<MPhase> ph(f->prog_head[D - 1].n_phases);
+        cudaMemcpy(tr.data(), ws.trace, 4096 * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaMemcpy(ph.data(), f->prog_head[D - 1].phases, ph.size() * sizeof(MPhase), cudaMemcpyDeviceToHost);
+        double sum[5] = {0, 0, 0, 0, 0};
+        int cnt[5] = {0, 0, 0, 0, 0};
+        double wsum[5] = {0, 0, 0, 0, 0};
+        for (size_t i = 0; i < ph.size(); i++) {
+            sum[ph[i].type] += (double)(tr[2 * i + 2] - tr[2 * i]);
+            wsum[ph[i].type] += (double)(tr[2 * i + 1] - tr[2 * i]);
+            cnt[ph[i].type]++;
+        }
+        const char* nm[5] = {"LN", "GEMM", "ATTN", "CODESUM", "ACT"};
+        for (int k = 0; k < 5; k++)
+            if (cnt[k]) fprintf(stderr, "[mega trace] %-8s n=%3d avg %.2f us (CTA0 own work %.2f us, barrier wait %.2f us)\n", nm[k], cnt[k],
+                                sum[k] / cnt[k] / 1e3, wsum[k] / cnt[k] / 1e3, (sum[k] - wsum[k]) / cnt[k] / 1e3);
+        for (size_t i = 0; i < ph.size() && i < 16; i++)
+            fprintf(stderr, "[mega trace] phase %2zu type %d N_out %5d K %5d splits %2d : %.2f us (work %.2f)\n", i, ph[i].type, ph[i].N_out,
+                    ph[i].K, ph[i].splits, (double)(tr[2 * i + 2] - tr[2 * i]) / 1e3, (double)(tr[2 * i + 1] - tr[2 * i]) / 1e3);
     }
     return 0;
 }

@@ -97,6 +97,38 @@ struct StepState {
 };
 int launch_sample_dyn(const float* logits, const StepState* stt, int d, int B, int V, int HW, int D, cudaStream_t st, bool pdl);
 
+enum { MP_LN = 0, MP_GEMM = 1, MP_ATTN = 2, MP_CODESUM = 3, MP_ACT = 4 };
+
+struct alignas(64) MPhase {
+    CUtensorMap tmW, tmX;                 // GEMM operands (W: [N_out,K] bf16 box 64x128; X: [B,K] bf16 box 64x64)
+    int type;
+    // ---- MP_LN: x_out = x_in + bias + sum_s partial[s] (+ extra) ; xn = LN(x_out)
+    const float* x_in; const float* partial; int S; const float* bias; const float* extra; float* x_out;
+    const float* g; const float* be; __nv_bfloat16* xn;
+    // ---- MP_GEMM
+    int N_out, K, splits, mode;           // mode: GT_F32 | GT_BF16_GELU | GT_PARTIAL
+    const float* gbias; float bias_scale;
+    const float* res; const int* res_row_ptr; long long res_row_stride, ld_res;
+    void* out; float* gpartial;
+    // ---- MP_ATTN
+    const float* apart; int aS; const float* bqkv; __nv_bfloat16 *kc, *vc, *att; int Tmax; const int* t_ptr; int t_host;
+    // ---- MP_CODESUM
+    int cs_mode; __nv_bfloat16* cs_out;
+};
+
+struct MegaParams {
+    const MPhase* phases;
+    int n_phases;
+    int B, E, nh;
+    unsigned* bar;                        // [0] monotonic arrive counter, [1] base for the next launch
+    const StepState* stt;
+    const float* codebook; int HW, D, Kc, C;
+    long long* trace;                     // optional [n_phases + 1] globaltimer stamps of CTA 0 (RQB200_MEGA_TRACE=1)
+};
+
+size_t mega_smem_bytes(int E);
+int launch_ar_mega(const MegaParams& P, int n_sm, cudaStream_t st);
+
 struct ArFast;
 ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, const rqb200_block_weights* body,
                        const rqb200_block_weights* head);

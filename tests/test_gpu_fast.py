@@ -71,16 +71,28 @@ def test_fast_tier_free_running_consistency(golden, layouts):
     skip = (h0 * bs[1] + w0) * bs[2]
     c = model._native_sample(a, aux, cond, (h0, w0), 1.0, 100, 0.95, True, noise=noise[skip:].contiguous())
     assert torch.equal(c, a)
-    # CUDA graphs and PDL are pure scheduling: same codes without them
-    for var in ("RQB200_NO_GRAPH", "RQB200_NO_PDL"):
-        os.environ[var] = "1"
-        try:
-            model._invalidate_native()
-            d = model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=noise)
-        finally:
-            del os.environ[var]
-            model._invalidate_native()
-        assert torch.equal(a, d), var
+    # CUDA graphs and PDL are pure scheduling: same codes without them (persistent form and per-op chain alike)
+    for mega in ("1", "0"):
+        os.environ["RQB200_MEGA"] = mega
+        model._invalidate_native()
+        base = model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=noise)
+        for var in ("RQB200_NO_GRAPH", "RQB200_NO_PDL"):
+            os.environ[var] = "1"
+            try:
+                model._invalidate_native()
+                d = model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=noise)
+            finally:
+                del os.environ[var]
+                model._invalidate_native()
+            assert torch.equal(base, d), (var, mega)
+    # persistent form vs per-op chain: same arithmetic up to the LayerNorm reduction order
+    _, lg_chain = model._native_sample(a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a)
+    os.environ["RQB200_MEGA"] = "1"
+    model._invalidate_native()
+    _, lg_mega = model._native_sample(a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a)
+    del os.environ["RQB200_MEGA"]
+    model._invalidate_native()
+    assert float((lg_chain - lg_mega).abs().max()) < 2e-2 * float(lg_mega.std())
 
 
 def test_fast_tier_text_conditioned_prefill(golden, layouts):

@@ -248,6 +248,7 @@ struct ArFast {
     int B = 0;
     CUtensorMap tx_xn, tx_att, tx_h, tx_s;
     cudaGraphExec_t g_cond = nullptr, g_code = nullptr, g_head = nullptr;
+    int64_t n_nodes[3] = {0, 0, 0};      // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
     bool use_graph = true, use_pdl = true;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
@@ -525,7 +526,10 @@ static int capture(ArFast& f, FastWs& ws, int which, cudaGraphExec_t* out) {
     if (!f.cap_stream) RQB_CUDA(cudaStreamCreateWithFlags(&f.cap_stream, cudaStreamNonBlocking));
     cudaStream_t st = f.cap_stream;
     RQB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int64_t before = g_launches;
     int rc = which == 0 ? record_body(f, ws, true, st) : which == 1 ? record_body(f, ws, false, st) : record_head(f, ws, st);
+    f.n_nodes[which] = g_launches - before;
+    g_launches = before;                   // recording is not launching
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(RQB200_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
@@ -633,7 +637,7 @@ int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B
                                                                                         : record_head(*f, ws, st);
         if (!*g) RQB_TRY(capture(*f, ws, which, g));
         RQB_CUDA(cudaGraphLaunch(*g, st));
-        g_launches++;
+        g_launches += f->n_nodes[which];     // kernels executed by this replay
         return 0;
     };
     // prefill: cond tokens, then (resume) the code tokens of positions < idx0, one cached step each -- causal, so

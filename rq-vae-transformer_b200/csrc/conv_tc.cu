@@ -275,43 +275,69 @@ __device__ __forceinline__ void store_split4(__half* hi, __half* lo, const float
     }
 }
 
+// one thread per (image, group): reduce the per-chunk fp64 partial sums once (instead of once per apply CTA)
+__global__ void gn_finalize_kernel(double* __restrict__ part, int B, int nchunks, double n, double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 32) return;
+    const int b = i / 32, g = i % 32;
+    double ts = 0.0, tss = 0.0;
+    for (int c = 0; c < nchunks; c++) {
+        const double* o = part + (((int64_t)b * nchunks + c) * 32 + g) * 2;
+        ts += o[0];
+        tss += o[1];
+    }
+    double mean = ts / n, var = tss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double* fin = part + (int64_t)B * nchunks * 64 + (int64_t)i * 2;
+    fin[0] = mean;
+    fin[1] = 1.0 / sqrt(var + eps);
+}
+
 // GroupNorm apply (+SiLU) from the fp64 partial statistics of gn_stats_kernel, writing the fp16 NHWC conv operand
 __global__ void __launch_bounds__(256) gn_apply_f16_kernel(const float* __restrict__ X, const double* __restrict__ part,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            __half* __restrict__ Y, __half* __restrict__ Ylo, int HW, int C,
                                                            float eps, int silu, int nchunks) {
     __shared__ float s_mean[32], s_rstd[32];
-    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
     const int cg = C / 32;
-    if (warp == 0) {
-        double ts = 0.0, tss = 0.0;
-        for (int c = 0; c < nchunks; c++) {
-            const double* o = part + (((int64_t)b * nchunks + c) * 32 + lane) * 2;
-            ts += o[0];
-            tss += o[1];
-        }
-        double n = (double)HW * cg, mean = ts / n, var = tss / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[lane] = (float)mean;
-        s_rstd[lane] = (float)(1.0 / sqrt(var + (double)eps));
+    if (threadIdx.x < 32) {                                        // finalised by gn_finalize_kernel: (mean, rstd) per (b, group)
+        const double* fin = part + (int64_t)gridDim.y * nchunks * 64 + ((int64_t)b * 32 + threadIdx.x) * 2;
+        s_mean[threadIdx.x] = (float)fin[0];
+        s_rstd[threadIdx.x] = (float)fin[1];
     }
     __syncthreads();
-    // thread <-> 4 consecutive channels; consecutive threads cover one pixel's channels, then the next pixel
-    const int c4n = C / 4;
-    const int64_t total4 = (int64_t)HW * c4n;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256) {
-        const int c = (int)(i % c4n) * 4;
-        const int g = c / cg;                                     // cg % 4 == 0 -> the 4 channels share a group
-        const float4 x = *reinterpret_cast<const float4*>(X + (int64_t)b * HW * C + i * 4);
-        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-        const float mean = s_mean[g], rstd = s_rstd[g];
-        float v[4] = {(x.x - mean) * rstd * ga.x + be.x, (x.y - mean) * rstd * ga.y + be.y, (x.z - mean) * rstd * ga.z + be.z,
-                      (x.w - mean) * rstd * ga.w + be.w};
+    (void)eps;
+    // thread <-> 8 consecutive channels (two float4 loads, one 16 B store per output tensor); 32-bit indexing per image
+    const int c8n = C / 8;
+    const unsigned total8 = (unsigned)HW * (unsigned)c8n;
+    const float* Xb = X + (int64_t)b * HW * C;
+    __half* Yb = Y + (int64_t)b * HW * C;
+    __half* Lb = Ylo ? Ylo + (int64_t)b * HW * C : nullptr;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total8; i += gridDim.x * 256u) {
+        const int c = (int)(i % (unsigned)c8n) * 8;
+        const float4 x0 = __ldcs(reinterpret_cast<const float4*>(Xb + (size_t)i * 8));
+        const float4 x1 = __ldcs(reinterpret_cast<const float4*>(Xb + (size_t)i * 8 + 4));
+        const float4 ga0 = *reinterpret_cast<const float4*>(gamma + c), ga1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+        const float4 be0 = *reinterpret_cast<const float4*>(beta + c), be1 = *reinterpret_cast<const float4*>(beta + c + 4);
+        const int g0 = c / cg, g1 = (c + 4) / cg;                 // cg % 4 == 0 -> each half shares a group
+        const float m0 = s_mean[g0], r0 = s_rstd[g0], m1 = s_mean[g1], r1 = s_rstd[g1];
+        float v[8] = {(x0.x - m0) * r0 * ga0.x + be0.x, (x0.y - m0) * r0 * ga0.y + be0.y, (x0.z - m0) * r0 * ga0.z + be0.z,
+                      (x0.w - m0) * r0 * ga0.w + be0.w, (x1.x - m1) * r1 * ga1.x + be1.x, (x1.y - m1) * r1 * ga1.y + be1.y,
+                      (x1.z - m1) * r1 * ga1.z + be1.z, (x1.w - m1) * r1 * ga1.w + be1.w};
         if (silu) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = v[k] / (1.0f + __expf(-v[k]));
+            for (int k = 0; k < 8; k++) v[k] = v[k] / (1.0f + __expf(-v[k]));
         }
-        store_split4(Y + (int64_t)b * HW * C + i * 4, Ylo ? Ylo + (int64_t)b * HW * C + i * 4 : nullptr, v);
+        __half2 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+            const float2 f = __half22float2(h[k]);
+            l[k] = __floats2half2_rn(v[2 * k] - f.x, v[2 * k + 1] - f.y);
+        }
+        *reinterpret_cast<uint4*>(Yb + (size_t)i * 8) = *reinterpret_cast<uint4*>(h);
+        if (Lb) *reinterpret_cast<uint4*>(Lb + (size_t)i * 8) = *reinterpret_cast<uint4*>(l);
     }
 }
 
@@ -337,7 +363,9 @@ int launch_groupnorm_f16(const float* X, const float* gamma, const float* beta, 
     if (C % 128 != 0) return fail(RQB200_EINVAL, "groupnorm_f16: C % 128 != 0");
     const int nchunks = (int)ceil_div(HW, 256);
     RQB_TRY(launch_gn_stats(X, stats_ws, B, HW, C, st));
-    int gx = (int)std::min<int64_t>(ceil_div((int64_t)HW * C / 4, 256), 2048);
+    gn_finalize_kernel<<<(unsigned)ceil_div(B * 32, 128), 128, 0, st>>>(stats_ws, B, nchunks, (double)HW * (C / 32), 1e-6);
+    RQB_TRY(check_launch("gn_finalize"));
+    int gx = (int)std::min<int64_t>(ceil_div((int64_t)HW * C / 8, 256), 1024);
     gn_apply_f16_kernel<<<dim3(gx, B), 256, 0, st>>>(X, stats_ws, gamma, beta, (__half*)Y16, (__half*)Y16lo, HW, C, 1e-6f, silu, nchunks);
     return check_launch("gn_apply_f16");
 }

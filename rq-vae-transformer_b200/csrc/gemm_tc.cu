@@ -218,7 +218,7 @@ int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcP
     switch (bn) {
         case 16: return launch_gemm_tc_t<16, 8>(tmW, tmX, p, pdl, st);
         case 32: return launch_gemm_tc_t<32, 8>(tmW, tmX, p, pdl, st);
-        case 64: return launch_gemm_tc_t<64, 8>(tmW, tmX, p, pdl, st);
+        case 64: return getenv("RQB200_GEMM_STAGES4") ? launch_gemm_tc_t<64, 4>(tmW, tmX, p, pdl, st) : launch_gemm_tc_t<64, 8>(tmW, tmX, p, pdl, st);
         case 128: return launch_gemm_tc_t<128, 6>(tmW, tmX, p, pdl, st);
         default: return launch_gemm_tc_t<256, 4>(tmW, tmX, p, pdl, st);
     }

@@ -10,6 +10,7 @@ Arithmetic tiers: ``amp=False`` -> 'exact' (fp32 weights/activations, FFMA -- th
 defined on); ``amp=True`` -> 'fast' (bf16 weights on tcgen05 tensor cores, fp32 accumulate; the reference's own amp
 path is fp16 autocast).  ``self.precision`` ('exact' | 'fast') or RQB200_PRECISION overrides the ``amp`` mapping."""
 import ctypes as C
+import os
 from collections import OrderedDict
 from itertools import product
 
@@ -129,9 +130,15 @@ class RQTransformer(Stage2Model):
             return q.codebooks[0].weight[:-1]
         raise NotImplementedError("rqb200: model_aux must be an RQ-VAE with a shared codebook")
 
-    def _engine(self, codebook, mode):
+    def _engine(self, codebook, mode, slot=0):
         dev = self.pos_emb_hw.device
-        key = (str(dev), mode, codebook.data_ptr())
+        key = (str(dev), mode, codebook.data_ptr(), slot)
+        if key not in self._eng and slot > 0:
+            # engines of one model share the packed weights of slot 0; each slot owns its workspace, KV cache and graphs
+            base = self._engine(codebook, mode, 0)
+            eng = {"handle": base["make"](), "keep": base["keep"], "ws": None, "make": base["make"]}
+            self._eng[key] = eng
+            return eng
         if key in self._eng:
             return self._eng[key]
         N.require_cuda(self.pos_emb_hw, codebook)
@@ -182,10 +189,16 @@ class RQTransformer(Stage2Model):
         w.codebook = f32(codebook)
         body, head = blocks(self.body_transformer), blocks(self.head_transformer)
         w.body, w.head = C.cast(body, C.POINTER(N.BlockWeights)), C.cast(head, C.POINTER(N.BlockWeights))
-        handle = L.rqb200_ar_create(C.byref(cfg), C.byref(w))
-        if not handle:
-            raise N.NativeError("rqb200_ar_create: " + L.rqb200_last_error().decode())
-        eng = {"handle": handle, "keep": keep, "ws": None}
+        keep.extend([body, head, cfg, w])
+
+        def make():
+            hnd = L.rqb200_ar_create(C.byref(cfg), C.byref(w))
+            if not hnd:
+                raise N.NativeError("rqb200_ar_create: " + L.rqb200_last_error().decode())
+            return hnd
+
+        handle = make()
+        eng = {"handle": handle, "keep": keep, "ws": None, "make": make}
         self._eng[key] = eng
         return eng
 
@@ -223,12 +236,20 @@ class RQTransformer(Stage2Model):
         dev = self.pos_emb_hw.device
         N.require_cuda(partial, cond, self.pos_emb_hw)
         ks, ps = self._lists(top_k, top_p)
-        eng = self._engine(self._codebook_of(model_aux, D), self._mode(amp))
+        codebook = self._codebook_of(model_aux, D)
+        mode = self._mode(amp)
         partial = partial.to(torch.int64).contiguous()
         cond_t = None if cond is None else cond.reshape(B, self.block_size_cond).to(torch.int64).contiguous()
         idx0 = start_loc[0] * W + start_loc[1]
         n_tok = max(H * W - idx0, 0) * D
         V = self.vocab_size[0]
+        # the step is latency-bound, not throughput-bound: independent sub-batches on separate streams overlap each other's
+        # kernel latencies (fast tier only; RQB200_AR_STREAMS -- default 1: measured slower at 2 and 4 because the GEMM kernels
+        # own every SM's shared memory)
+        n_streams = 1
+        if mode == N.MODE_FAST and not return_logits and force_codes is None:
+            n_streams = int(os.environ.get("RQB200_AR_STREAMS", "1"))
+            n_streams = max(1, min(n_streams, B // 8 if B >= 8 else 1))
         with torch.cuda.device(dev):
             if noise is None:
                 # one exponential_ per token, in (h,w,d) order: the draws torch.multinomial would make (utils.py:114)
@@ -239,18 +260,41 @@ class RQTransformer(Stage2Model):
                 noise = None
             logits = torch.empty(n_tok, B, V, dtype=torch.float32, device=dev) if return_logits else None
             out = torch.empty_like(partial)
-            need = N.lib().rqb200_ar_workspace_bytes(eng["handle"], B)
-            if eng["ws"] is None or eng["ws"].numel() < need:
-                eng["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
             kk = (C.c_int32 * D)(*[int(k) for k in ks])
             pp = (C.c_float * D)(*[float(p) for p in ps])
             fc = None if force_codes is None else force_codes.to(torch.int64).contiguous()
-            N.check(N.lib().rqb200_ar_sample(eng["handle"], N.ptr(partial), N.ptr(cond_t), B, int(start_loc[0]),
-                                             int(start_loc[1]), float(temperature), kk, pp, N.ptr(noise),
-                                             0 if noise is None else B * V, N.ptr(logits), N.ptr(fc), N.ptr(out),
-                                             N.ptr(eng["ws"]), eng["ws"].numel(), N.stream_ptr(dev)), "ar_sample")
-        self.last_launches = N.lib().rqb200_ar_last_launches(eng["handle"])
-        N.launch_count["total"] += self.last_launches
+            bounds = [(i * B // n_streams, (i + 1) * B // n_streams) for i in range(n_streams)]
+            cur = torch.cuda.current_stream(dev)
+            launches = 0
+            for slot, (lo, hi) in enumerate(bounds):
+                eng = self._engine(codebook, mode, slot)
+                nb = hi - lo
+                need = N.lib().rqb200_ar_workspace_bytes(eng["handle"], nb)
+                if eng["ws"] is None or eng["ws"].numel() < need:
+                    eng["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+                if n_streams > 1:
+                    if "stream" not in eng:
+                        eng["stream"] = torch.cuda.Stream(dev)
+                    st = eng["stream"]
+                    st.wait_stream(cur)
+                else:
+                    st = cur
+
+                def off(t, row_elems, esize):
+                    return C.c_void_p(t.data_ptr() + lo * row_elems * esize) if t is not None else C.c_void_p(0)
+
+                HWD = H * W * D
+                N.check(N.lib().rqb200_ar_sample(
+                    eng["handle"], off(partial, HWD, 8), off(cond_t, self.block_size_cond, 8), nb, int(start_loc[0]),
+                    int(start_loc[1]), float(temperature), kk, pp, off(noise, V, 4), 0 if noise is None else B * V,
+                    off(logits, V, 4), off(fc, HWD, 8), off(out, HWD, 8), N.ptr(eng["ws"]), eng["ws"].numel(),
+                    C.c_void_p(st.cuda_stream)), "ar_sample")
+                launches += N.lib().rqb200_ar_last_launches(eng["handle"])
+            if n_streams > 1:
+                for slot in range(n_streams):
+                    cur.wait_stream(self._engine(codebook, mode, slot)["stream"])
+        self.last_launches = launches
+        N.launch_count["total"] += launches
         return (out, logits) if return_logits else out
 
     @torch.no_grad()

@@ -255,6 +255,10 @@ struct ArFast {
     // persistent ("mega") form: phase programs living in the workspace
     bool want_mega = false, use_mega = false;   // opt-in (RQB200_MEGA=1): measured slower than the PDL chain so far, see DESIGN.md
     int mega_split_fc1 = 3;
+    // cluster (DSMEM) split-K for proj / fc1 / fc2: the GEMM itself emits x += ..., h = gelu(...) -- no partial round trip
+    bool cluster = false;        // all of proj/fc1/fc2 (measured slower than split-K partials + fused LN reduction: 289 vs 243 ms)
+    bool fc1_cluster = false;    // fc1 only (RQB200_FC1_CLUSTER=2|3|4): also slower (311-319 ms) -- cluster launches cost more than they save here
+    int cl_proj = 8, cl_fc1 = 2, cl_fc2 = 8;
     int n_sm = 148;
     MegaParams prog_cond = {}, prog_code = {}, prog_head[8] = {};
 };
@@ -324,6 +328,27 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
     const int64_t per = (int64_t)B * c.n_head * Tmax * 64;
     for (size_t l = 0; l < blocks.size(); l++) {
         const rqb200_block_weights& bw = blocks[l];
+        if (f.cluster) {
+            // ---- cluster split-K form: 6 kernels per block, no partial buffers except for qkv
+            const bool first = l == 0;
+            const bool need_copy = first && (x_src != x || pending_extra != nullptr);
+            RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)(first ? x_src : x),
+                               (const float*)nullptr, 0, (const float*)nullptr, (const float*)(first ? pending_extra : nullptr),
+                               (float*)(need_copy ? x : nullptr), (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
+            RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+                         nullptr, 0, st));
+            RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
+                               (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
+                               c.n_head, Tmax, t_ptr, t_host));
+            RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.cl_proj, GT_F32, bw.bproj, 1.f, x, nullptr, x, E, nullptr, 0, st));
+            RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)x,
+                               (const float*)nullptr, 0, (const float*)nullptr, (const float*)nullptr, (float*)nullptr,
+                               (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
+            RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.cl_fc1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr,
+                         0, st));
+            RQB_TRY(gemm(f, maps[l].fc2, f.tx_h, E, 4 * E, B, f.cl_fc2, GT_F32, bw.b2, 1.f, x, nullptr, x, E, nullptr, 0, st));
+            continue;
+        }
         // LN1 (+ pending fc2 reduction of the previous block / previous stack)
         const bool pend = l > 0 || first_has_pending;
         const float* pb = l > 0 ? blocks[l - 1].b2 : pending_bias;
@@ -342,8 +367,9 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
                            (const float*)ws.P, f.split_proj, (const float*)bw.bproj, (const float*)nullptr, x,
                            (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
         if (f.split_fc1 == 1) {
-            RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, 1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr,
-                         0, st));
+            // fc1: either one CTA per 128-feature tile (48 CTAs at E=1536) or a 2-CTA cluster per tile with DSMEM reduction
+            RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.fc1_cluster ? f.cl_fc1 : 1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr,
+                         nullptr, 0, nullptr, 0, st));
         } else {
             RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
                          nullptr, 0, st));
@@ -510,8 +536,9 @@ static int record_head(ArFast& f, FastWs& ws, cudaStream_t st) {
         }
         // classifier: LN(x + pending fc2) -> logits                                              (transformers.py:278-285)
         RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)ws.XH,
-                           (const float*)ws.P, f.split_fc2, (const float*)f.head.back().b2, (const float*)nullptr,
-                           (float*)nullptr, w.cls_ln_w, w.cls_ln_b, ws.XN, B, E));
+                           (const float*)(f.cluster ? nullptr : ws.P), f.cluster ? 0 : f.split_fc2,
+                           (const float*)(f.cluster ? nullptr : f.head.back().b2), (const float*)nullptr, (float*)nullptr, w.cls_ln_w,
+                           w.cls_ln_b, ws.XN, B, E));
         RQB_TRY(gemm(f, f.tm_cls, f.tx_xn, V, E, B, 1, GT_F32, w.b_cls, 1.f, ws.LOGITS, nullptr, nullptr, 0, nullptr, 0, st));
         RQB_TRY(launch_pdl(logits_copy_kernel, dim3(64), dim3(256), 0, st, f.use_pdl, (const StepState*)ws.state,
                            (const float*)ws.LOGITS, d, (int64_t)B * V));
@@ -560,6 +587,11 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     if ((e = getenv("RQB200_NO_GRAPH")) && e[0] == '1') f->use_graph = false;
     if ((e = getenv("RQB200_NO_PDL")) && e[0] == '1') f->use_pdl = false;
     if ((e = getenv("RQB200_MEGA")) && e[0] == '1') f->want_mega = true;
+    if ((e = getenv("RQB200_CLUSTER")) && e[0] == '1') f->cluster = true;
+    if ((e = getenv("RQB200_FC1_CLUSTER"))) { f->cl_fc1 = atoi(e); f->fc1_cluster = f->cl_fc1 > 1; }
+    f->cl_proj = std::min(8, E / 64);
+    f->cl_fc2 = std::min(8, 4 * E / 64);
+    f->cl_fc1 = std::min(f->cl_fc1, E / 64);
     if ((e = getenv("RQB200_MEGA_SPLIT_FC1"))) f->mega_split_fc1 = atoi(e);
     f->mega_split_fc1 = pick_split(4 * E / 128, E / 64, f->mega_split_fc1);
     {

@@ -71,7 +71,28 @@ constexpr int GT_A_BYTES = 128 * 64 * 2;     // 128 output features x 64 k, bf16
 
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN, int STAGES>
+// CL == true: the `splits` CTAs of one output tile form a thread-block cluster; instead of writing fp32 partials to global
+// memory they stage them in their own shared memory, and after a cluster barrier CTA r sums rows [r*rp, (r+1)*rp) of the
+// tile over all peers through distributed shared memory (fixed peer order -> deterministic) and applies the epilogue.
+// Removes the partial round trip through L2 and the reduction work from the consumer kernel.
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_map(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    return ra;
+}
+// not volatile / no memory clobber on purpose: the S loads of one element are independent and must be allowed to overlap;
+// ordering against the producers' stores is provided by the cluster barriers around the reduction
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+    float v;
+    asm("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
+    return v;
+}
+
+template <int BN, int STAGES, bool CL>
 __global__ void __launch_bounds__(GT_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, GemmTcParams p) {
     constexpr int B_BYTES = BN * 64 * 2;
@@ -149,6 +170,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         tc::mbar_wait(tmem_full, 0);
         tc::tc_fence_after();
         const bool nvalid = n < p.N_out;
+        if (CL) {
+            float* stg = reinterpret_cast<float*>(smem);                    // [128][BN + 1] fp32, over the drained ring
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16];
+                tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) stg[(q * 32 + lane) * (BN + 1) + c0 + i] = __uint_as_float(r[i]);
+            }
+        } else {
         const float bias = (p.bias != nullptr && nvalid && p.mode != GT_PARTIAL) ? p.bias[n] * p.bias_scale : 0.f;
         const float* res = nullptr;
         if (p.mode == GT_F32 && p.residual != nullptr)
@@ -181,18 +213,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
             }
         }
+        }
+    }
+    if (CL) {
+        __syncwarp();
+        cluster_sync_all();                                                 // every CTA of the tile has staged its partial
+        tc::pdl_wait();
+        const int S = p.splits, rp = (128 + S - 1) / S;
+        const int r0 = split * rp, r1 = (r0 + rp) < 128 ? (r0 + rp) : 128;
+        const uint32_t stg_u32 = tc::smem_u32(smem);
+        const float* res = nullptr;
+        if (p.mode == GT_F32 && p.residual != nullptr)
+            res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0);
+        const int total = (r1 - r0) * p.B;
+        uint32_t peer[8];
+#pragma unroll
+        for (int pr = 0; pr < 8; pr++) peer[pr] = dsmem_map(stg_u32, (uint32_t)(pr < S ? pr : 0));
+        for (int idx = threadIdx.x; idx < total; idx += GT_THREADS) {
+            // consecutive threads -> consecutive output features (coalesced stores); b is the slow index
+            const int row = r0 + idx % (r1 - r0), b = idx / (r1 - r0);
+            const int n = tile * 128 + row;
+            const uint32_t off = (uint32_t)(row * (BN + 1) + b) * 4u;
+            float part[8];
+#pragma unroll
+            for (int pr = 0; pr < 8; pr++) part[pr] = pr < S ? ld_dsmem_f32(peer[pr] + off) : 0.f;
+            float v = 0.f;
+#pragma unroll
+            for (int pr = 0; pr < 8; pr++) v += part[pr];                       // fixed order: deterministic
+            if (p.bias) v += p.bias[n] * p.bias_scale;
+            if (p.mode == GT_F32) {
+                if (res) v += res[(int64_t)b * p.ld_res + n];
+                reinterpret_cast<float*>(p.out)[(int64_t)b * p.ld_out + n] = v;
+            } else if (p.mode == GT_BF16_GELU) {
+                reinterpret_cast<__nv_bfloat16*>(p.out)[(int64_t)b * p.ld_out + n] = __float2bfloat16(gelu_erf_f(v));
+            } else {
+                reinterpret_cast<__nv_bfloat16*>(p.out)[(int64_t)b * p.ld_out + n] = __float2bfloat16(v);
+            }
+        }
+        __syncwarp();
+        cluster_sync_all();                                                 // peers may still be reading this CTA's staging area
     }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool CL>
 static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (GT_A_BYTES + BN * 128) + 1024 + 256;
+    static_assert(!CL || (size_t)STAGES * (GT_A_BYTES + BN * 128) >= (size_t)128 * (BN + 1) * 4, "staging area must fit in the ring");
     static bool attr = false;
     if (!attr) {
-        RQB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RQB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -200,12 +272,19 @@ static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, cons
     cfg.blockDim = dim3(GT_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    RQB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES>, tmW, tmX, p));
+    if (CL) {
+        at[1].id = cudaLaunchAttributeClusterDimension;
+        at[1].val.clusterDim.x = (unsigned)p.splits;
+        at[1].val.clusterDim.y = 1;
+        at[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
+    RQB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, CL>, tmW, tmX, p));
     g_launches++;
     return 0;
 }
@@ -215,12 +294,22 @@ int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcP
     if (p.B < 1 || p.B > 256) return fail(RQB200_EINVAL, "gemm_tc: batch rows must be in [1,256]");
     if (p.splits < 1 || p.splits > p.K / 64) return fail(RQB200_EINVAL, "gemm_tc: bad split count");
     const int bn = gemm_tc_bn(p.B);
+    if (p.splits > 1 && p.mode != GT_PARTIAL) {          // split-K with an in-kernel (cluster / DSMEM) reduction
+        if (p.splits > 8) return fail(RQB200_EINVAL, "gemm_tc: cluster split-K supports at most 8 splits");
+        switch (bn) {
+            case 16: return launch_gemm_tc_t<16, 8, true>(tmW, tmX, p, pdl, st);
+            case 32: return launch_gemm_tc_t<32, 8, true>(tmW, tmX, p, pdl, st);
+            case 64: return launch_gemm_tc_t<64, 8, true>(tmW, tmX, p, pdl, st);
+            case 128: return launch_gemm_tc_t<128, 6, true>(tmW, tmX, p, pdl, st);
+            default: return launch_gemm_tc_t<256, 4, true>(tmW, tmX, p, pdl, st);
+        }
+    }
     switch (bn) {
-        case 16: return launch_gemm_tc_t<16, 8>(tmW, tmX, p, pdl, st);
-        case 32: return launch_gemm_tc_t<32, 8>(tmW, tmX, p, pdl, st);
-        case 64: return getenv("RQB200_GEMM_STAGES4") ? launch_gemm_tc_t<64, 4>(tmW, tmX, p, pdl, st) : launch_gemm_tc_t<64, 8>(tmW, tmX, p, pdl, st);
-        case 128: return launch_gemm_tc_t<128, 6>(tmW, tmX, p, pdl, st);
-        default: return launch_gemm_tc_t<256, 4>(tmW, tmX, p, pdl, st);
+        case 16: return launch_gemm_tc_t<16, 8, false>(tmW, tmX, p, pdl, st);
+        case 32: return launch_gemm_tc_t<32, 8, false>(tmW, tmX, p, pdl, st);
+        case 64: return launch_gemm_tc_t<64, 8, false>(tmW, tmX, p, pdl, st);
+        case 128: return launch_gemm_tc_t<128, 6, false>(tmW, tmX, p, pdl, st);
+        default: return launch_gemm_tc_t<256, 4, false>(tmW, tmX, p, pdl, st);
     }
 }
 
@@ -238,6 +327,6 @@ extern "C" int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const 
     GemmTcParams p = {};
     p.N_out = N_out; p.K = K; p.B = B; p.splits = splits;
     p.bias = bias; p.bias_scale = 1.f; p.residual = residual; p.ld_res = N_out; p.out = out; p.ld_out = N_out; p.partial = partial;
-    p.mode = splits > 1 ? GT_PARTIAL : (out_is_bf16 ? (gelu ? GT_BF16_GELU : GT_BF16) : GT_F32);
+    p.mode = (splits > 1 && partial != nullptr) ? GT_PARTIAL : (out_is_bf16 ? (gelu ? GT_BF16_GELU : GT_BF16) : GT_F32);
     return launch_gemm_tc(tw, tx, p, false, (cudaStream_t)stream);
 }

@@ -44,6 +44,31 @@ def test_gemm_tc_matches_fp32_matmul(N_out, K, B, splits):
         torch.testing.assert_close(part.sum(0), ref, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("N_out,K,B,splits", [(1536, 1536, 64, 8), (6144, 1536, 64, 2), (1536, 6144, 64, 8), (384, 512, 5, 4),
+                                               (4608, 1536, 64, 4), (1536, 1536, 16, 3), (2048, 1024, 128, 2)])
+def test_gemm_tc_cluster_splitk(N_out, K, B, splits):
+    """split-K reduced inside the kernel through distributed shared memory (thread-block clusters)"""
+    g = torch.Generator().manual_seed(N_out * 3 + K + B)
+    W = (torch.randn(N_out, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(DEV)
+    X = torch.randn(B, K, generator=g).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(N_out, generator=g).to(DEV)
+    R = torch.randn(B, N_out, generator=g).to(DEV)
+    ref = X.float() @ W.float().t()
+    L = N.lib()
+    out = torch.full((B, N_out), float("nan"), device=DEV)
+    N.check(L.rqb200_dbg_gemm_tc(N.ptr(W), N.ptr(X), N.ptr(bias), N.ptr(R), N.ptr(out), 0, 0, None, N_out, K, B, splits, N.stream_ptr()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, ref + bias + R, rtol=1e-4, atol=1e-4)
+    outb = torch.empty(B, N_out, device=DEV, dtype=torch.bfloat16)
+    N.check(L.rqb200_dbg_gemm_tc(N.ptr(W), N.ptr(X), N.ptr(bias), None, N.ptr(outb), 1, 1, None, N_out, K, B, splits, N.stream_ptr()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(outb.float(), gelu(ref + bias).to(torch.bfloat16).float(), rtol=2e-2, atol=2e-2)
+    out2 = torch.empty_like(out)
+    N.check(L.rqb200_dbg_gemm_tc(N.ptr(W), N.ptr(X), N.ptr(bias), N.ptr(R), N.ptr(out2), 0, 0, None, N_out, K, B, splits, N.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2), "cluster reduction is not deterministic"
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,ks,nchw,res", [
     (2, 8, 8, 256, 512, 3, 0, 0), (3, 16, 16, 512, 512, 1, 0, 1), (1, 64, 64, 256, 256, 3, 0, 1),
     (2, 256, 256, 128, 128, 3, 0, 1), (2, 256, 256, 128, 3, 3, 1, 0), (5, 8, 8, 512, 1536, 1, 0, 0),

@@ -87,18 +87,35 @@ ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ parti
             xn[(int64_t)b * E + e] = __float2bfloat16((row[e] - mean) * rstd * g[e] + be[e]);
 }
 
-// h = bf16(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K)
+// h = bf16(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K); 4 elements per thread, all partial loads in flight
 __global__ void __launch_bounds__(256)
 act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, __nv_bfloat16* __restrict__ h, int B,
                   int N) {
     tc::pdl_launch_dependents();
     tc::pdl_wait();
-    const int64_t total = (int64_t)B * N;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        int n = (int)(i % N);
-        float v = bias[n];
-        for (int s = 0; s < S; s++) v += partial[(int64_t)s * total + i];
-        h[i] = __float2bfloat16(0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)));
+    const int64_t total4 = (int64_t)B * N / 4;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256) {
+        const int n = (int)((i * 4) % N);
+        float4 pr[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+            if (s < S) pr[s] = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)s * B * N) + i);
+        float4 v = *reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+            if (s < S) { v.x += pr[s].x; v.y += pr[s].y; v.z += pr[s].z; v.w += pr[s].w; }
+        for (int s = 4; s < S; s++) {
+            float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)s * B * N) + i);
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = 0.5f * r[k] * (1.0f + erff(r[k] * 0.70710678118654752440f));
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(r[0], r[1]), h1 = __floats2bfloat162_rn(r[2], r[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&h0);
+        pk.y = *reinterpret_cast<unsigned*>(&h1);
+        *reinterpret_cast<uint2*>(h + i * 4) = pk;
     }
 }
 
@@ -256,6 +273,7 @@ struct ArFast {
     bool want_mega = false, use_mega = false;   // opt-in (RQB200_MEGA=1): measured slower than the PDL chain so far, see DESIGN.md
     int mega_split_fc1 = 3;
     // cluster (DSMEM) split-K for proj / fc1 / fc2: the GEMM itself emits x += ..., h = gelu(...) -- no partial round trip
+    int skip = 0;                // diagnostics only (RQB200_SKIP bitmask): drop a kernel type from the chain to measure its in-situ cost
     bool cluster = false;        // all of proj/fc1/fc2 (measured slower than split-K partials + fused LN reduction: 289 vs 243 ms)
     bool fc1_cluster = false;    // fc1 only (RQB200_FC1_CLUSTER=2|3|4): also slower (311-319 ms) -- cluster launches cost more than they save here
     int cl_proj = 8, cl_fc1 = 2, cl_fc2 = 8;
@@ -352,31 +370,31 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
         // LN1 (+ pending fc2 reduction of the previous block / previous stack)
         const bool pend = l > 0 || first_has_pending;
         const float* pb = l > 0 ? blocks[l - 1].b2 : pending_bias;
-        RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl,
+        if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl,
                            (const float*)(l == 0 ? x_src : x), (const float*)(pend ? ws.P : nullptr), pend ? f.split_fc2 : 0,
                            (const float*)(pend ? pb : nullptr), (const float*)(l == 0 ? pending_extra : nullptr), x,
                            (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
-        RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+        if (!(f.skip & 2)) RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
                      nullptr, 0, st));
-        RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
+        if (!(f.skip & 4)) RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
                            (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
                            c.n_head, Tmax, t_ptr, t_host));
-        RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+        if (!(f.skip & 8)) RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
                      nullptr, 0, st));
-        RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)x,
+        if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)x,
                            (const float*)ws.P, f.split_proj, (const float*)bw.bproj, (const float*)nullptr, x,
                            (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
         if (f.split_fc1 == 1) {
             // fc1: either one CTA per 128-feature tile (48 CTAs at E=1536) or a 2-CTA cluster per tile with DSMEM reduction
-            RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.fc1_cluster ? f.cl_fc1 : 1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr,
+            if (!(f.skip & 16)) RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.fc1_cluster ? f.cl_fc1 : 1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr,
                          nullptr, 0, nullptr, 0, st));
         } else {
             RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
                          nullptr, 0, st));
-            RQB_TRY(launch_pdl(act_reduce_kernel, dim3(148), dim3(256), 0, st, f.use_pdl, (const float*)ws.P, f.split_fc1,
+            RQB_TRY(launch_pdl(act_reduce_kernel, dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)B * 4 * E / 4, 256), 1184)), dim3(256), 0, st, f.use_pdl, (const float*)ws.P, f.split_fc1,
                                (const float*)bw.b1, ws.Hh, B, 4 * E));
         }
-        RQB_TRY(gemm(f, maps[l].fc2, f.tx_h, E, 4 * E, B, f.split_fc2, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+        if (!(f.skip & 32)) RQB_TRY(gemm(f, maps[l].fc2, f.tx_h, E, 4 * E, B, f.split_fc2, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
                      nullptr, 0, st));
     }
     return 0;
@@ -588,6 +606,7 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     if ((e = getenv("RQB200_NO_PDL")) && e[0] == '1') f->use_pdl = false;
     if ((e = getenv("RQB200_MEGA")) && e[0] == '1') f->want_mega = true;
     if ((e = getenv("RQB200_CLUSTER")) && e[0] == '1') f->cluster = true;
+    if ((e = getenv("RQB200_SKIP"))) f->skip = atoi(e);
     if ((e = getenv("RQB200_FC1_CLUSTER"))) { f->cl_fc1 = atoi(e); f->fc1_cluster = f->cl_fc1 > 1; }
     f->cl_proj = std::min(8, E / 64);
     f->cl_fc2 = std::min(8, 4 * E / 64);
@@ -602,7 +621,7 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     const int nkbE = E / 64;
     f->split_qkv = pick_split(3 * E / 128, nkbE, getenv("RQB200_SPLIT_QKV") ? atoi(getenv("RQB200_SPLIT_QKV")) : 0);
     f->split_proj = pick_split(E / 128, nkbE, getenv("RQB200_SPLIT_PROJ") ? atoi(getenv("RQB200_SPLIT_PROJ")) : 0);
-    f->split_fc1 = pick_split(4 * E / 128, nkbE, getenv("RQB200_SPLIT_FC1") ? atoi(getenv("RQB200_SPLIT_FC1")) : 1);
+    f->split_fc1 = pick_split(4 * E / 128, nkbE, getenv("RQB200_SPLIT_FC1") ? atoi(getenv("RQB200_SPLIT_FC1")) : 0);
     f->split_fc2 = pick_split(E / 128, 4 * nkbE, getenv("RQB200_SPLIT_FC2") ? atoi(getenv("RQB200_SPLIT_FC2")) : 0);
     auto mk = [&](const std::vector<rqb200_block_weights>& bl, std::vector<FastLayer>& out) -> int {
         out.resize(bl.size());

@@ -89,8 +89,12 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise
             const unsigned int prefix = sel_prefix;
             const unsigned int himask = (pass == 3) ? 0u : (0xffffffffu << (shift + 8));
             for (int i = t; i < V; i += SMP_THREADS) {
-                uint32_t k = f2key(xs[i]);
-                if ((k & himask) == (prefix & himask)) atomicAdd(&hist[(k >> shift) & 0xffu], 1u);
+                // warp-aggregated histogram update: logits share few exponent values, so the top digits collide heavily
+                const uint32_t k = f2key(xs[i]);
+                const bool hit = (k & himask) == (prefix & himask);
+                const unsigned bkt = hit ? ((k >> shift) & 0xffu) : (0x100u + (unsigned)lane);
+                const unsigned peers = __match_any_sync(__activemask(), bkt);
+                if (hit && lane == __ffs(peers) - 1) atomicAdd(&hist[bkt], (unsigned)__popc(peers));
             }
             __syncthreads();
             if (t == 0) {

@@ -79,38 +79,75 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise
     for (int i = t; i < V; i += SMP_THREADS) xs[i] = lg[i] / temperature;
     __syncthreads();
 
-    // ---- 2. top-k threshold by radix select (k-th largest key)
+    // ---- 2. top-k threshold: exact k-th largest by an 8-pass, 4-bit radix select.  No shared-memory atomics and no
+    // MATCH: every thread keeps its <= 16 order-preserving keys in registers, counts the 16 digit values in packed
+    // 16-bit lanes (8 words), the warp reduces them with shuffles, one word per thread sums the 32 warps.
     if (top_k > 0 && top_k < V) {
-        if (t == 0) { sel_prefix = 0u; sel_remaining = (unsigned)top_k; }
-        for (int pass = 3; pass >= 0; pass--) {
-            for (int i = t; i < 256; i += SMP_THREADS) hist[i] = 0u;
-            __syncthreads();
-            const int shift = pass * 8;
-            const unsigned int prefix = sel_prefix;
-            const unsigned int himask = (pass == 3) ? 0u : (0xffffffffu << (shift + 8));
-            for (int i = t; i < V; i += SMP_THREADS) {
-                // warp-aggregated histogram update: logits share few exponent values, so the top digits collide heavily
-                const uint32_t k = f2key(xs[i]);
-                const bool hit = (k & himask) == (prefix & himask);
-                const unsigned bkt = hit ? ((k >> shift) & 0xffu) : (0x100u + (unsigned)lane);
-                const unsigned peers = __match_any_sync(__activemask(), bkt);
-                if (hit && lane == __ffs(peers) - 1) atomicAdd(&hist[bkt], (unsigned)__popc(peers));
-            }
-            __syncthreads();
-            if (t == 0) {
-                unsigned int rem = sel_remaining, b = 255;
-                for (;; b--) {            // walk buckets from the largest digit down
-                    unsigned int c = hist[b];
-                    if (c >= rem) break;
-                    rem -= c;
-                    if (b == 0) break;
-                }
-                sel_prefix = prefix | (b << shift);
-                sel_remaining = rem;
-            }
-            __syncthreads();
+        uint32_t keys[16];
+        uint32_t valid = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int i = t + j * SMP_THREADS;
+            keys[j] = 0u;
+            if (i < V) { keys[j] = f2key(xs[i]); valid |= 1u << j; }
         }
-        const float kth = key2f(sel_prefix);
+        uint32_t* whist = reinterpret_cast<uint32_t*>(hist);           // [32 warps][8 packed words]
+        uint32_t prefix = 0u, rem = (uint32_t)top_k;
+#pragma unroll 1
+        for (int pass = 7; pass >= 0; pass--) {
+            const int shift = pass * 4;
+            const uint32_t himask = (pass == 7) ? 0u : (0xffffffffu << (shift + 4));
+            // 16 four-bit counters per 64-bit word; two words (keys 0-7 / 8-15) so that no counter can exceed 8
+            unsigned long long acc0 = 0ull, acc1 = 0ull;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const bool hit = ((valid >> j) & 1u) && ((keys[j] & himask) == (prefix & himask));
+                const unsigned long long inc = hit ? (1ull << (4u * ((keys[j] >> shift) & 15u))) : 0ull;
+                if (j < 8) acc0 += inc; else acc1 += inc;
+            }
+            uint32_t cnt[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t e = (uint32_t)((acc0 >> (8 * w)) & 0xffull), o2 = (uint32_t)((acc1 >> (8 * w)) & 0xffull);
+                // byte w holds digits 2w (low nibble) and 2w+1 (high nibble)
+                cnt[w] = ((e & 15u) + (o2 & 15u)) | (((e >> 4) + (o2 >> 4)) << 16);
+            }
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt[w] += __shfl_xor_sync(0xffffffffu, cnt[w], o);   // <= 512 per half: no carry
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int w = 0; w < 8; w++) whist[wid * 8 + w] = cnt[w];
+            }
+            __syncthreads();
+            if (wid == 0) {
+                // lane l < 8 sums packed word l over the 32 warps (<= 16384 per half: fits 16 bits when V <= 16384... use 2 x 32-bit)
+                uint32_t lo = 0u, hi = 0u;
+                if (lane < 8) {
+                    for (int w2 = 0; w2 < SMP_THREADS / 32; w2++) {
+                        const uint32_t v = whist[w2 * 8 + lane];
+                        lo += v & 0xffffu;
+                        hi += v >> 16;
+                    }
+                }
+                // digit 2*lane -> lo, 2*lane+1 -> hi ; walk digits 15..0 accumulating from the top
+                uint32_t acc = 0u, digit = 0u, newrem = rem;
+                bool found = false;
+#pragma unroll
+                for (int dgt = 15; dgt >= 0; dgt--) {
+                    const uint32_t c = __shfl_sync(0xffffffffu, (dgt & 1) ? hi : lo, dgt >> 1);
+                    if (!found && acc + c >= rem) { digit = (uint32_t)dgt; newrem = rem - acc; found = true; }
+                    if (!found) acc += c;
+                }
+                if (lane == 0) { sel_prefix = prefix | (digit << shift); sel_remaining = newrem; }
+            }
+            __syncthreads();
+            prefix = sel_prefix;
+            rem = sel_remaining;
+        }
+        const float kth = key2f(prefix);
         for (int i = t; i < V; i += SMP_THREADS) {
             float v = xs[i];
             if (v < kth) xs[i] = -INFINITY;            // out[out < v[:, [-1]]] = -inf  (utils.py:63)

@@ -31,7 +31,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), or None
-TRAFFIC_NCU = {"gemm_tc_fc2": None}
+TRAFFIC_NCU = {"gemm_tc_fc2": 19702016}   # profiles/ncu_gemm_tc_r1_raw.csv, fc2 launch: 19.70 MB read + 0 B written (partials stay in L2)
 
 METRIC = "256x256 images/sec (ImageNet 1.4B RQ-Transformer, 8x8x4 codes, K=16384, top-k 1024, sample+decode)"
 

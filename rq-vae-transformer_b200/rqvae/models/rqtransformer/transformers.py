@@ -264,10 +264,16 @@ class RQTransformer(Stage2Model):
             pp = (C.c_float * D)(*[float(p) for p in ps])
             fc = None if force_codes is None else force_codes.to(torch.int64).contiguous()
             bounds = [(i * B // n_streams, (i + 1) * B // n_streams) for i in range(n_streams)]
+            if mode == N.MODE_FAST and n_streams == 1 and B > 256:
+                # the tcgen05 tier takes at most 256 batch rows per call (UMMA N <= 256): run equal chunks back to back
+                if return_logits:
+                    raise N.NativeError("rqb200: return_logits with B > 256 is not supported on the fast tier")
+                n_chunks = -(-B // 256)
+                bounds = [(i * B // n_chunks, (i + 1) * B // n_chunks) for i in range(n_chunks)]
             cur = torch.cuda.current_stream(dev)
             launches = 0
             for slot, (lo, hi) in enumerate(bounds):
-                eng = self._engine(codebook, mode, slot)
+                eng = self._engine(codebook, mode, slot if n_streams > 1 else 0)
                 nb = hi - lo
                 need = N.lib().rqb200_ar_workspace_bytes(eng["handle"], nb)
                 if eng["ws"] is None or eng["ws"].numel() < need:

@@ -20,8 +20,7 @@ bench.MODELS["prof"] = tuple(m)
 torch.set_grad_enabled(False)
 dev = torch.device("cuda", 0)
 ar, vae, dd = bench.build_models("prof", dev, prec, tiny_vae=True)
-from tests.helpers import CodebookAux  # noqa: E402
-aux = CodebookAux(vae.quantizer._shared_table())
+aux = vae          # the RQ-VAE itself supplies the shared codebook (model_aux.get_code_emb_with_depth path)
 part = torch.zeros(B, H, W, 4, dtype=torch.long, device=dev)
 cond = torch.randint(0, 1000, (B, 1), device=dev)
 for it in range(3):

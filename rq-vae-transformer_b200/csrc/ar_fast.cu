@@ -47,44 +47,63 @@ __global__ void __launch_bounds__(384)
 ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int S, const float* __restrict__ bias,
                  const float* __restrict__ extra, float* __restrict__ x_out, const float* __restrict__ g,
                  const float* __restrict__ be, __nv_bfloat16* __restrict__ xn, int B, int E) {
-    extern __shared__ float row[];
+    // each thread owns up to 3 float4 chunks of the row (E <= 384*4*3); every load is issued before the first dependent add and
+    // the row stays in registers between the statistics and the normalisation
     __shared__ float red[33];
     tc::pdl_launch_dependents();
     tc::pdl_wait();
     const int b = blockIdx.x;
     const int E4 = E >> 2;
+    const int S12 = S < 12 ? S : 12;
+    float4 v[3];
     float s = 0.f;
-    for (int e4 = threadIdx.x; e4 < E4; e4 += blockDim.x) {
-        float4 v = x_in ? reinterpret_cast<const float4*>(x_in + (int64_t)b * E)[e4] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) { float4 t = reinterpret_cast<const float4*>(bias)[e4]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-        // split-K partials: issue the loads in batches of 4 (independent), add in a fixed order (deterministic)
-        int i = 0;
-        for (; i + 4 <= S; i += 4) {
-            float4 p0 = reinterpret_cast<const float4*>(partial + ((int64_t)(i + 0) * B + b) * E)[e4];
-            float4 p1 = reinterpret_cast<const float4*>(partial + ((int64_t)(i + 1) * B + b) * E)[e4];
-            float4 p2 = reinterpret_cast<const float4*>(partial + ((int64_t)(i + 2) * B + b) * E)[e4];
-            float4 p3 = reinterpret_cast<const float4*>(partial + ((int64_t)(i + 3) * B + b) * E)[e4];
-            v.x += p0.x; v.y += p0.y; v.z += p0.z; v.w += p0.w;
-            v.x += p1.x; v.y += p1.y; v.z += p1.z; v.w += p1.w;
-            v.x += p2.x; v.y += p2.y; v.z += p2.z; v.w += p2.w;
-            v.x += p3.x; v.y += p3.y; v.z += p3.z; v.w += p3.w;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int e4 = threadIdx.x + k * 384;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e4 < E4) {
+            float4 pr[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++)
+                if (i < S12) pr[i] = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
+            if (x_in) v[k] = reinterpret_cast<const float4*>(x_in + (int64_t)b * E)[e4];
+            if (bias) { float4 t = reinterpret_cast<const float4*>(bias)[e4]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
+#pragma unroll
+            for (int i = 0; i < 12; i++)
+                if (i < S12) { v[k].x += pr[i].x; v[k].y += pr[i].y; v[k].z += pr[i].z; v[k].w += pr[i].w; }
+            for (int i = 12; i < S; i++) {
+                float4 p0 = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
+                v[k].x += p0.x; v[k].y += p0.y; v[k].z += p0.z; v[k].w += p0.w;
+            }
+            if (extra) { float4 t = reinterpret_cast<const float4*>(extra)[e4]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
+            if (x_out) reinterpret_cast<float4*>(x_out + (int64_t)b * E)[e4] = v[k];
+            s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
         }
-        for (; i < S; i++) {
-            float4 p0 = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
-            v.x += p0.x; v.y += p0.y; v.z += p0.z; v.w += p0.w;
-        }
-        if (extra) { float4 t = reinterpret_cast<const float4*>(extra)[e4]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-        reinterpret_cast<float4*>(row)[e4] = v;
-        s += (v.x + v.y) + (v.z + v.w);
-        if (x_out) reinterpret_cast<float4*>(x_out + (int64_t)b * E)[e4] = v;
     }
     const float mean = block_sum(s, red) / (float)E;
     float q = 0.f;
-    for (int e = threadIdx.x; e < E; e += blockDim.x) { float d = row[e] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (threadIdx.x + k * 384 < E4) {
+            const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+            q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+        }
     const float rstd = rsqrtf(block_sum(q, red) / (float)E + 1e-5f);
-    if (xn)
-        for (int e = threadIdx.x; e < E; e += blockDim.x)
-            xn[(int64_t)b * E + e] = __float2bfloat16((row[e] - mean) * rstd * g[e] + be[e]);
+    if (xn) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int e4 = threadIdx.x + k * 384;
+            if (e4 < E4) {
+                const float4 gg = reinterpret_cast<const float4*>(g)[e4], bb = reinterpret_cast<const float4*>(be)[e4];
+                __nv_bfloat162 h0 = __floats2bfloat162_rn((v[k].x - mean) * rstd * gg.x + bb.x, (v[k].y - mean) * rstd * gg.y + bb.y);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn((v[k].z - mean) * rstd * gg.z + bb.z, (v[k].w - mean) * rstd * gg.w + bb.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<unsigned*>(&h0);
+                pk.y = *reinterpret_cast<unsigned*>(&h1);
+                reinterpret_cast<uint2*>(xn + (int64_t)b * E)[e4] = pk;
+            }
+        }
+    }
 }
 
 // h = bf16(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K); 4 elements per thread, all partial loads in flight
@@ -140,6 +159,7 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     float2 q = make_float2(bqkv[c], bqkv[c + 1]);
     float2 k = make_float2(bqkv[E + c], bqkv[E + c + 1]);
     float2 v = make_float2(bqkv[2 * E + c], bqkv[2 * E + c + 1]);
+#pragma unroll 4
     for (int s = 0; s < S; s++) {
         const float* p = part + ((int64_t)s * B + b) * 3 * E;
         float2 a = *reinterpret_cast<const float2*>(p + c);
@@ -189,7 +209,19 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     __syncwarp();
     const float inv = 1.0f / sum;
     float2 o = make_float2(e_new * vf.x, e_new * vf.y);
-    for (int j = 0; j < t; j++) {
+    int j = 0;
+    for (; j + 8 <= t; j += 8) {                          // 8 independent V rows in flight
+        __nv_bfloat162 raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) raw[u] = *reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)(j + u) * 64 + 2 * lane);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const float2 vv = __bfloat1622float2(raw[u]);
+            o.x = fmaf(ps[wq][j + u], vv.x, o.x);
+            o.y = fmaf(ps[wq][j + u], vv.y, o.y);
+        }
+    }
+    for (; j < t; j++) {
         const float p = ps[wq][j];
         float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)j * 64 + 2 * lane));
         o.x = fmaf(p, vv.x, o.x);
@@ -350,7 +382,7 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
             // ---- cluster split-K form: 6 kernels per block, no partial buffers except for qkv
             const bool first = l == 0;
             const bool need_copy = first && (x_src != x || pending_extra != nullptr);
-            RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)(first ? x_src : x),
+            RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)(first ? x_src : x),
                                (const float*)nullptr, 0, (const float*)nullptr, (const float*)(first ? pending_extra : nullptr),
                                (float*)(need_copy ? x : nullptr), (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
             RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
@@ -359,7 +391,7 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
                                (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
                                c.n_head, Tmax, t_ptr, t_host));
             RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.cl_proj, GT_F32, bw.bproj, 1.f, x, nullptr, x, E, nullptr, 0, st));
-            RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)x,
+            RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x,
                                (const float*)nullptr, 0, (const float*)nullptr, (const float*)nullptr, (float*)nullptr,
                                (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
             RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.cl_fc1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr,
@@ -370,7 +402,7 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
         // LN1 (+ pending fc2 reduction of the previous block / previous stack)
         const bool pend = l > 0 || first_has_pending;
         const float* pb = l > 0 ? blocks[l - 1].b2 : pending_bias;
-        if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl,
+        if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl,
                            (const float*)(l == 0 ? x_src : x), (const float*)(pend ? ws.P : nullptr), pend ? f.split_fc2 : 0,
                            (const float*)(pend ? pb : nullptr), (const float*)(l == 0 ? pending_extra : nullptr), x,
                            (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
@@ -381,7 +413,7 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
                            c.n_head, Tmax, t_ptr, t_host));
         if (!(f.skip & 8)) RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
                      nullptr, 0, st));
-        if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)x,
+        if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x,
                            (const float*)ws.P, f.split_proj, (const float*)bw.bproj, (const float*)nullptr, x,
                            (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
         if (f.split_fc1 == 1) {
@@ -553,7 +585,7 @@ static int record_head(ArFast& f, FastWs& ws, cudaStream_t st) {
                                st));
         }
         // classifier: LN(x + pending fc2) -> logits                                              (transformers.py:278-285)
-        RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)E * 4, st, f.use_pdl, (const float*)ws.XH,
+        RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)ws.XH,
                            (const float*)(f.cluster ? nullptr : ws.P), f.cluster ? 0 : f.split_fc2,
                            (const float*)(f.cluster ? nullptr : f.head.back().b2), (const float*)nullptr, (float*)nullptr, w.cls_ln_w,
                            w.cls_ln_b, ws.XN, B, E));
@@ -595,8 +627,8 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
                        const rqb200_block_weights* head_p) {
     std::vector<rqb200_block_weights> body(body_p, body_p + cfg.n_body), head(head_p, head_p + cfg.n_head_layers);
     const int E = cfg.embed_dim;
-    if (E % 128 != 0 || cfg.vocab % 128 != 0 || cfg.code_dim % 64 != 0 || cfg.D > 8 || cfg.cond_len + cfg.H * cfg.W > AF_MAXT) {
-        set_error("ar fast tier: need E % 128 == 0, V % 128 == 0, code_dim % 64 == 0, D <= 8, cond_len + H*W <= 512");
+    if (E % 128 != 0 || cfg.vocab % 128 != 0 || cfg.code_dim % 64 != 0 || cfg.D > 8 || cfg.cond_len + cfg.H * cfg.W > AF_MAXT || E > 4608) {
+        set_error("ar fast tier: need E % 128 == 0, V % 128 == 0, code_dim % 64 == 0, D <= 8, cond_len + H*W <= 512, E <= 4608");
         return nullptr;
     }
     ArFast* f = new ArFast();

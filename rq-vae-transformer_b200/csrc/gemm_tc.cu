@@ -185,17 +185,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const float* res = nullptr;
         if (p.mode == GT_F32 && p.residual != nullptr)
             res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0);
+        // issue the TMEM loads of up to 64 columns back to back, wait once
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t r[16];
-            tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        for (int cb = 0; cb < BN; cb += 64) {
+            uint32_t r4[4][16];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (cb + c * 16 < BN) tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb + c * 16), r4[c]);
             tc::tmem_ld_wait();
             if (!nvalid) continue;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+            const int c0 = cb + c * 16;
+            if (c0 >= BN) break;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int b = c0 + i;
                 if (b >= p.B) break;
-                float v = __uint_as_float(r[i]) + bias;
+                float v = __uint_as_float(r4[c][i]) + bias;
                 switch (p.mode) {
                     case GT_F32:
                         if (res) v += res[(int64_t)b * p.ld_res + n];
@@ -211,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         p.partial[((int64_t)split * p.B + b) * p.N_out + n] = v;
                         break;
                 }
+            }
             }
         }
         }

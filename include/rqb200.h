@@ -36,6 +36,9 @@ extern "C" {
 /* arithmetic modes (DESIGN.md "two modes") */
 #define RQB200_MODE_EXACT 0  /* fp32 weights + fp32 FFMA: the bit-exact-indices gate                    */
 #define RQB200_MODE_FAST 1   /* bf16 (AR) / fp16 (conv) operands on tcgen05, fp32 accumulate: throughput */
+/* OR-ed into rqb200_ar_config.mode (fast tier): every weight matrix [N,K] is stored tile-major, [N/128][K/64][128][64], so that
+ * each 128x64 TMA box is 16 KB of CONTIGUOUS HBM (a row-major matrix gives 128 scattered 128 B segments per box) */
+#define RQB200_WEIGHTS_TILED 0x100
 
 const char* rqb200_last_error(void);
 int rqb200_version(void);
@@ -151,7 +154,9 @@ int64_t rqb200_vae_last_launches(const rqb200_vae* h);
  * Single-kernel entry points used by tests/ and bench.py's roofline leg; not part of the reference-facing surface.
  * rqb200_dbg_gemm_tc: one launch of the tcgen05 weight-streaming GEMM (csrc/gemm_tc.cu):
  *   out[b, n] = act(sum_k W[n,k] X[b,k] + bias[n]) (+ residual[b,n]);  W [N_out,K] bf16, X [B,K] bf16;
- *   splits > 1: partial [splits,B,N_out] f32 receives the per-split sums instead (no act / residual). */
+ *   splits > 1: partial [splits,B,N_out] f32 receives the per-split sums instead (no act / residual); partial == NULL with
+ *   splits > 1 reduces inside the kernel (thread-block cluster, <= 8 splits).  splits < 0: W is tile-major (RQB200_WEIGHTS_TILED)
+ *   and |splits| is the split count. */
 int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out,
                        int out_is_bf16, int gelu, float* partial, int N_out, int K, int B, int splits, void* stream);
 

@@ -147,7 +147,7 @@ rqb200_ar* rqb200_ar_create(const rqb200_ar_config* cfg, const rqb200_ar_weights
     h->head.assign(w->head, w->head + cfg->n_head_layers);
     h->w.body = h->body.data();
     h->w.head = h->head.data();
-    if (cfg->mode == RQB200_MODE_FAST) {
+    if ((cfg->mode & 0xff) == RQB200_MODE_FAST) {
         if (cfg->weight_dtype != RQB200_BF16) { rqb::set_error("ar_create: fast tier needs bf16 weights"); delete h; return nullptr; }
         h->fast = rqb::ar_fast_create(h->cfg, h->w, h->body.data(), h->head.data());
         if (!h->fast) { delete h; return nullptr; }

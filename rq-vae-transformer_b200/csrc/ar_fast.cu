@@ -305,6 +305,7 @@ struct ArFast {
     bool want_mega = false, use_mega = false;   // opt-in (RQB200_MEGA=1): measured slower than the PDL chain so far, see DESIGN.md
     int mega_split_fc1 = 3;
     // cluster (DSMEM) split-K for proj / fc1 / fc2: the GEMM itself emits x += ..., h = gelu(...) -- no partial round trip
+    bool w_tiled = false;        // weights packed tile-major by the host binding (cfg.weight_layout)
     int skip = 0;                // diagnostics only (RQB200_SKIP bitmask): drop a kernel type from the chain to measure its in-situ cost
     bool cluster = false;        // all of proj/fc1/fc2 (measured slower than split-K partials + fused LN reduction: 289 vs 243 ms)
     bool fc1_cluster = false;    // fc1 only (RQB200_FC1_CLUSTER=2|3|4): also slower (311-319 ms) -- cluster launches cost more than they save here
@@ -364,6 +365,7 @@ static int gemm(const ArFast& f, const CUtensorMap& tw, const CUtensorMap& tx, i
     p.N_out = N_out; p.K = K; p.B = B; p.splits = splits; p.mode = mode;
     p.bias = bias; p.bias_scale = bias_scale; p.out = out; p.ld_out = N_out; p.partial = partial;
     p.residual = residual; p.ld_res = ld_res; p.res_row_ptr = res_row_ptr; p.res_row_stride = res_row_stride;
+    p.w_tiled = f.w_tiled ? 1 : 0;
     return launch_gemm_tc(tw, tx, p, f.use_pdl, st);
 }
 
@@ -454,6 +456,7 @@ static int build_programs(ArFast& f, FastWs& ws) {
                   float bias_scale, void* out, const float* res, int64_t ld_res, const int* res_row_ptr, int64_t res_row_stride) {
         MPhase p = {};
         p.type = MP_GEMM; p.tmW = tw; p.tmX = tx; p.N_out = N_out; p.K = K; p.splits = splits; p.mode = mode; p.gbias = bias;
+        p.w_tiled = f.w_tiled ? 1 : 0;
         p.bias_scale = bias_scale; p.out = out; p.gpartial = ws.P; p.res = res; p.ld_res = ld_res; p.res_row_ptr = res_row_ptr;
         p.res_row_stride = res_row_stride;
         all.push_back(p);
@@ -633,6 +636,7 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     }
     ArFast* f = new ArFast();
     f->cfg = cfg; f->w = w; f->body = body; f->head = head;
+    f->w_tiled = (cfg.mode & 0x100) != 0;              // bit 8 of `mode`: fast-tier weights are tile-major
     const char* e;
     if ((e = getenv("RQB200_NO_GRAPH")) && e[0] == '1') f->use_graph = false;
     if ((e = getenv("RQB200_NO_PDL")) && e[0] == '1') f->use_pdl = false;
@@ -658,18 +662,18 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     auto mk = [&](const std::vector<rqb200_block_weights>& bl, std::vector<FastLayer>& out) -> int {
         out.resize(bl.size());
         for (size_t l = 0; l < bl.size(); l++) {
-            RQB_TRY(make_tmap_2d(&out[l].qkv, bl[l].wqkv, 1, E, 3 * E, (uint64_t)E * 2, 64, 128));
-            RQB_TRY(make_tmap_2d(&out[l].proj, bl[l].wproj, 1, E, E, (uint64_t)E * 2, 64, 128));
-            RQB_TRY(make_tmap_2d(&out[l].fc1, bl[l].w1, 1, E, 4 * E, (uint64_t)E * 2, 64, 128));
-            RQB_TRY(make_tmap_2d(&out[l].fc2, bl[l].w2, 1, 4 * E, E, (uint64_t)E * 8, 64, 128));
+            RQB_TRY(make_tmap_weight(&out[l].qkv, bl[l].wqkv, 3 * E, E, f->w_tiled));
+            RQB_TRY(make_tmap_weight(&out[l].proj, bl[l].wproj, E, E, f->w_tiled));
+            RQB_TRY(make_tmap_weight(&out[l].fc1, bl[l].w1, 4 * E, E, f->w_tiled));
+            RQB_TRY(make_tmap_weight(&out[l].fc2, bl[l].w2, E, 4 * E, f->w_tiled));
         }
         return 0;
     };
     int rc = mk(body, f->lbody);
     if (!rc) rc = mk(head, f->lhead);
-    if (!rc) rc = make_tmap_2d(&f->tm_win, w.w_in, 1, cfg.code_dim, E, (uint64_t)cfg.code_dim * 2, 64, 128);
-    if (!rc) rc = make_tmap_2d(&f->tm_whead, w.w_head, 1, cfg.code_dim, E, (uint64_t)cfg.code_dim * 2, 64, 128);
-    if (!rc) rc = make_tmap_2d(&f->tm_cls, w.w_cls, 1, E, cfg.vocab, (uint64_t)E * 2, 64, 128);
+    if (!rc) rc = make_tmap_weight(&f->tm_win, w.w_in, E, cfg.code_dim, f->w_tiled);
+    if (!rc) rc = make_tmap_weight(&f->tm_whead, w.w_head, E, cfg.code_dim, f->w_tiled);
+    if (!rc) rc = make_tmap_weight(&f->tm_cls, w.w_cls, cfg.vocab, E, f->w_tiled);
     if (rc) { delete f; return nullptr; }
     return f;
 }

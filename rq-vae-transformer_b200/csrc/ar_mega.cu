@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) ar_mega_kernel(MegaParams P) {
                         const int s = wc % MG_WSTAGES;
                         tc::mbar_wait(&empty_w[s], ((wc / MG_WSTAGES) & 1) ^ 1);
                         tc::mbar_expect_tx(&full_w[s], MG_A_BYTES);
-                        tc::tma_load_2d(wring + s * MG_A_BYTES, &ph.tmW, &full_w[s], kb * 64, tile * 128, tc::L2_EVICT_FIRST);
+                        tc::tma_load_2d(wring + s * MG_A_BYTES, &ph.tmW, &full_w[s], ph.w_tiled ? 0 : kb * 64,
+                                        ph.w_tiled ? (tile * nkb_total + kb) * 128 : tile * 128, tc::L2_EVICT_FIRST);
                     }
                 }
             }

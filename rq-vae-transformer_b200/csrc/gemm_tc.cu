@@ -131,7 +131,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const int pre = nkb < STAGES ? nkb : STAGES;
             for (int i = 0; i < pre; i++) {
                 tc::mbar_expect_tx(&full[i], STAGE_BYTES);
-                tc::tma_load_2d(smem + i * STAGE_BYTES, &tmW, &full[i], (kb0 + i) * 64, tile * 128, tc::L2_EVICT_FIRST);
+                tc::tma_load_2d(smem + i * STAGE_BYTES, &tmW, &full[i], p.w_tiled ? 0 : (kb0 + i) * 64,
+                                p.w_tiled ? (tile * nkb_total + kb0 + i) * 128 : tile * 128, tc::L2_EVICT_FIRST);
             }
             tc::pdl_wait();
             for (int i = 0; i < pre; i++)
@@ -140,7 +141,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const int s = i % STAGES;
                 tc::mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
                 tc::mbar_expect_tx(&full[s], STAGE_BYTES);
-                tc::tma_load_2d(smem + s * STAGE_BYTES, &tmW, &full[s], (kb0 + i) * 64, tile * 128, tc::L2_EVICT_FIRST);
+                tc::tma_load_2d(smem + s * STAGE_BYTES, &tmW, &full[s], p.w_tiled ? 0 : (kb0 + i) * 64,
+                                p.w_tiled ? (tile * nkb_total + kb0 + i) * 128 : tile * 128, tc::L2_EVICT_FIRST);
                 tc::tma_load_2d(smem + s * STAGE_BYTES + GT_A_BYTES, &tmX, &full[s], (kb0 + i) * 64, 0, tc::L2_EVICT_LAST);
             }
         }
@@ -321,20 +323,31 @@ int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcP
     }
 }
 
+// weight tensor map: row-major [N_out, K], or tile-major [N_out/128][K/64][128][64] viewed as a 64-wide 2-D tensor
+int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K, bool tiled) {
+    if (tiled) return make_tmap_2d(out, W, 1, 64, (uint64_t)(N_out / 128) * (K / 64) * 128, 128, 64, 128);
+    return make_tmap_2d(out, W, 1, (uint64_t)K, (uint64_t)N_out, (uint64_t)K * 2, 64, 128);
+}
+
 }  // namespace rqb
 
 // ---- diagnostic entry point (tests/test_gpu_tc.py): one GEMM through the tcgen05 kernel
+
 extern "C" int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out,
                                   int out_is_bf16, int gelu, float* partial, int N_out, int K, int B, int splits,
                                   void* stream) {
     using namespace rqb;
     CUtensorMap tw, tx;
     const int bn = gemm_tc_bn(B);
-    RQB_TRY(make_tmap_2d(&tw, W_bf16, 1, (uint64_t)K, (uint64_t)N_out, (uint64_t)K * 2, 64, 128));
+    // splits < 0: W is tile-major ([N_out/128][K/64][128][64]) and |splits| is the split count
+    const bool tiled = splits < 0;
+    if (tiled) splits = -splits;
+    RQB_TRY(make_tmap_weight(&tw, W_bf16, N_out, K, tiled));
     RQB_TRY(make_tmap_2d(&tx, X_bf16, 1, (uint64_t)K, (uint64_t)B, (uint64_t)K * 2, 64, (uint32_t)bn));
     GemmTcParams p = {};
     p.N_out = N_out; p.K = K; p.B = B; p.splits = splits;
     p.bias = bias; p.bias_scale = 1.f; p.residual = residual; p.ld_res = N_out; p.out = out; p.ld_out = N_out; p.partial = partial;
+    p.w_tiled = tiled ? 1 : 0;
     p.mode = (splits > 1 && partial != nullptr) ? GT_PARTIAL : (out_is_bf16 ? (gelu ? GT_BF16_GELU : GT_BF16) : GT_F32);
     return launch_gemm_tc(tw, tx, p, false, (cudaStream_t)stream);
 }

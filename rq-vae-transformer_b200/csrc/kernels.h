@@ -73,8 +73,10 @@ struct GemmTcParams {
     void* out;                    // [B, ld_out] f32 / bf16
     int64_t ld_out;
     float* partial;               // GT_PARTIAL: [splits][B][N_out] f32 (no bias)
+    int w_tiled;                  // 1: W is stored tile-major [N_out/128][K/64][128][64] (each TMA box = 16 KB contiguous in HBM)
 };
 inline int gemm_tc_bn(int B) { return B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : B <= 128 ? 128 : 256; }
+int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K, bool tiled);
 int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st);
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes_log2, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
@@ -107,6 +109,7 @@ struct alignas(64) MPhase {
     const float* g; const float* be; __nv_bfloat16* xn;
     // ---- MP_GEMM
     int N_out, K, splits, mode;           // mode: GT_F32 | GT_BF16_GELU | GT_PARTIAL
+    int w_tiled;
     const float* gbias; float bias_scale;
     const float* res; const int* res_row_ptr; long long res_row_stride, ld_res;
     void* out; float* gpartial;

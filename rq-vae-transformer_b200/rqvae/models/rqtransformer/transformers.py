@@ -151,8 +151,14 @@ class RQTransformer(Stage2Model):
             keep.append(t)
             return t.data_ptr()
 
+        tiled = mode == N.MODE_FAST and os.environ.get("RQB200_TILED", "0") == "1"   # measured: no gain (latency-, not DRAM-page-bound)
+
         def wt(t):
             t = t.detach().to(wdt).contiguous()
+            if tiled:
+                # tile-major [N/128][K/64][128][64]: each TMA box of the weight streamer becomes 16 KB of contiguous HBM
+                n, k = t.shape
+                t = t.view(n // 128, 128, k // 64, 64).permute(0, 2, 1, 3).contiguous()
             keep.append(t)
             return t.data_ptr()
 
@@ -176,7 +182,7 @@ class RQTransformer(Stage2Model):
         cfg.vocab, cfg.H, cfg.W, cfg.D = self.vocab_size[0], self.block_size[0], self.block_size[1], self.block_size[2]
         cfg.vocab_cond, cfg.cond_len = self.vocab_size_cond, self.block_size_cond
         cfg.code_dim, cfg.codebook_size = codebook.shape[1], codebook.shape[0]
-        cfg.mode, cfg.weight_dtype = mode, N._DT[wdt]
+        cfg.mode, cfg.weight_dtype = (mode | 0x100) if tiled else mode, N._DT[wdt]
         if c.head.block.n_head != c.body.block.n_head:
             raise NotImplementedError("rqb200: body and head stacks must share n_head")
         w = N.ArWeights()

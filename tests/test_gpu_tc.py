@@ -44,6 +44,26 @@ def test_gemm_tc_matches_fp32_matmul(N_out, K, B, splits):
         torch.testing.assert_close(part.sum(0), ref, rtol=1e-4, atol=1e-4)
 
 
+def test_gemm_tc_tile_major_weights():
+    """RQB200_WEIGHTS_TILED: same product from the tile-major weight layout (every TMA box contiguous in HBM)"""
+    for (N_out, K, B, splits) in ((1536, 6144, 64, 12), (4608, 1536, 64, 4), (16384, 1536, 64, 1), (384, 128, 3, 1)):
+        g = torch.Generator().manual_seed(N_out + K)
+        W = (torch.randn(N_out, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(DEV)
+        X = torch.randn(B, K, generator=g).to(torch.bfloat16).to(DEV)
+        Wt = W.view(N_out // 128, 128, K // 64, 64).permute(0, 2, 1, 3).contiguous()
+        ref = X.float() @ W.float().t()
+        L = N.lib()
+        if splits == 1:
+            out = torch.empty(B, N_out, device=DEV)
+            N.check(L.rqb200_dbg_gemm_tc(N.ptr(Wt), N.ptr(X), None, None, N.ptr(out), 0, 0, None, N_out, K, B, -1, N.stream_ptr()))
+        else:
+            part = torch.empty(splits, B, N_out, device=DEV)
+            N.check(L.rqb200_dbg_gemm_tc(N.ptr(Wt), N.ptr(X), None, None, None, 0, 0, N.ptr(part), N_out, K, B, -splits, N.stream_ptr()))
+            out = part.sum(0)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
 @pytest.mark.parametrize("N_out,K,B,splits", [(1536, 1536, 64, 8), (6144, 1536, 64, 2), (1536, 6144, 64, 8), (384, 512, 5, 4),
                                                (4608, 1536, 64, 4), (1536, 1536, 16, 3), (2048, 1024, 128, 2)])
 def test_gemm_tc_cluster_splitk(N_out, K, B, splits):

@@ -210,12 +210,23 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     const float inv = 1.0f / sum;
     float2 o = make_float2(e_new * vf.x, e_new * vf.y);
     int j = 0;
-    for (; j + 8 <= t; j += 8) {                          // 8 independent V rows in flight
-        __nv_bfloat162 raw[8];
+    for (; j + 16 <= t; j += 16) {                        // 16 independent V rows in flight
+        __nv_bfloat162 raw[16];
 #pragma unroll
-        for (int u = 0; u < 8; u++) raw[u] = *reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)(j + u) * 64 + 2 * lane);
+        for (int u = 0; u < 16; u++) raw[u] = *reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)(j + u) * 64 + 2 * lane);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < 16; u++) {
+            const float2 vv = __bfloat1622float2(raw[u]);
+            o.x = fmaf(ps[wq][j + u], vv.x, o.x);
+            o.y = fmaf(ps[wq][j + u], vv.y, o.y);
+        }
+    }
+    for (; j + 4 <= t; j += 4) {
+        __nv_bfloat162 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) raw[u] = *reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)(j + u) * 64 + 2 * lane);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
             const float2 vv = __bfloat1622float2(raw[u]);
             o.x = fmaf(ps[wq][j + u], vv.x, o.x);
             o.y = fmaf(ps[wq][j + u], vv.y, o.y);

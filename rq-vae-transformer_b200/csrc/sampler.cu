@@ -123,15 +123,20 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise
             }
             __syncthreads();
             if (wid == 0) {
-                // lane l < 8 sums packed word l over the 32 warps (<= 16384 per half: fits 16 bits when V <= 16384... use 2 x 32-bit)
-                uint32_t lo = 0u, hi = 0u;
-                if (lane < 8) {
-                    for (int w2 = 0; w2 < SMP_THREADS / 32; w2++) {
-                        const uint32_t v = whist[w2 * 8 + lane];
-                        lo += v & 0xffffu;
-                        hi += v >> 16;
-                    }
+                // lane l holds warp l's 8 packed words; butterfly-add across lanes (totals <= 16384 per 16-bit half: no carry)
+                uint32_t tw[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) tw[w] = whist[lane * 8 + w];
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) tw[w] += __shfl_xor_sync(0xffffffffu, tw[w], o);
                 }
+                // digit 2w -> low half of word w, digit 2w+1 -> high half; give lane l (< 8) word l as before
+                uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+                for (int w = 0; w < 8; w++)
+                    if (lane == w) { lo = tw[w] & 0xffffu; hi = tw[w] >> 16; }
                 // digit 2*lane -> lo, 2*lane+1 -> hi ; walk digits 15..0 accumulating from the top
                 uint32_t acc = 0u, digit = 0u, newrem = rem;
                 bool found = false;

@@ -1,7 +1,9 @@
-from .configs import RQTransformerConfig
-from .transformers import RQTransformer
+"""Stage-2 prior: parameter tree + native AR engine binding (see transformers.py)."""
+from .configs import RQTransformerConfig  # noqa: F401  (re-exported for callers that build structured configs)
+from .transformers import RQTransformer  # noqa: F401
 
 
 def get_rqtransformer(config):
-    """reference: rqvae/models/rqtransformer/__init__.py:19-20"""
-    return RQTransformer(config)
+    """factory used by rqvae.models.create_model for ``type: rq-transformer`` (same role as the reference's getter)"""
+    model = RQTransformer(config)
+    return model

@@ -1,0 +1,1 @@
+"""Host-side helpers of the drop-in package: config layer, seeding/sampler wrapper, distributed wrapper."""

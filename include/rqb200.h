@@ -167,6 +167,14 @@ int rqb200_dbg_conv_tc(const void* X16, const void* W16, const void* X16lo, cons
                        const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ks, int out_nchw,
                        void* stream);
 
+/* rqb200_dbg_chain: micro-benchmark of ONE dependent stage (csrc/dbg_chain.cu), the quantity that bounds the cached AR step.
+ * mode 0: PDL chain of empty kernels in a CUDA graph; 1: PDL chain, every CTA reads 16 KB written by other CTAs of the previous
+ * kernel and writes 16 KB; 2: one persistent kernel, same data flow, grid-wide barrier between stages; 3: persistent, every CTA
+ * waits only for the `fan` producers it reads.  Runs `reps` timed repetitions of an `n_stages` chain on its own stream and
+ * returns microseconds per stage.  workspace (device): >= 2*ctas*16 KB + 4 KB + 4*ctas bytes. */
+int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, int smem_bytes, int fan, int reps, void* workspace,
+                     size_t workspace_bytes, float* us_per_stage);
+
 #ifdef __cplusplus
 }
 #endif

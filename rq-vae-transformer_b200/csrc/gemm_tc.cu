@@ -19,6 +19,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace rqb {
 
@@ -134,6 +135,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 tc::tma_load_2d(smem + i * STAGE_BYTES, &tmW, &full[i], p.w_tiled ? 0 : (kb0 + i) * 64,
                                 p.w_tiled ? (tile * nkb_total + kb0 + i) * 128 : tile * 128, tc::L2_EVICT_FIRST);
             }
+            if (p.l2pf)
+                for (int i = pre; i < nkb; i++)
+                    tc::tma_prefetch_2d(&tmW, p.w_tiled ? 0 : (kb0 + i) * 64,
+                                        p.w_tiled ? (tile * nkb_total + kb0 + i) * 128 : tile * 128);
             tc::pdl_wait();
             for (int i = 0; i < pre; i++)
                 tc::tma_load_2d(smem + i * STAGE_BYTES + GT_A_BYTES, &tmX, &full[i], (kb0 + i) * 64, 0, tc::L2_EVICT_LAST);
@@ -299,7 +304,9 @@ static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, cons
     return 0;
 }
 
-int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
+int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p_in, bool pdl, cudaStream_t st) {
+    GemmTcParams p = p_in;
+    if (const char* e = getenv("RQB200_GEMM_L2PF")) p.l2pf = atoi(e);
     if (p.K % 64 != 0 || p.N_out % 128 != 0) return fail(RQB200_EINVAL, "gemm_tc: need K % 64 == 0 and N_out % 128 == 0");
     if (p.B < 1 || p.B > 256) return fail(RQB200_EINVAL, "gemm_tc: batch rows must be in [1,256]");
     if (p.splits < 1 || p.splits > p.K / 64) return fail(RQB200_EINVAL, "gemm_tc: bad split count");
@@ -312,6 +319,21 @@ int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcP
             case 64: return launch_gemm_tc_t<64, 8, true>(tmW, tmX, p, pdl, st);
             case 128: return launch_gemm_tc_t<128, 6, true>(tmW, tmX, p, pdl, st);
             default: return launch_gemm_tc_t<256, 4, true>(tmW, tmX, p, pdl, st);
+        }
+    }
+    // RQB200_GEMM_STAGES (experiment): a shallower ring lets 2-3 GEMM CTAs of consecutive launches share an SM, so the
+    // next GEMM of the PDL chain prefetches its weights while the current one still runs.  Same k order -> same bits.
+    int stages = 8;
+    if (const char* e = getenv("RQB200_GEMM_STAGES")) stages = atoi(e);
+    if (bn <= 64 && stages != 8) {
+        if (bn == 64) {
+            if (stages == 3) return launch_gemm_tc_t<64, 3, false>(tmW, tmX, p, pdl, st);
+            if (stages == 4) return launch_gemm_tc_t<64, 4, false>(tmW, tmX, p, pdl, st);
+            if (stages == 6) return launch_gemm_tc_t<64, 6, false>(tmW, tmX, p, pdl, st);
+        } else if (bn == 32) {
+            if (stages == 3 || stages == 4) return launch_gemm_tc_t<32, 4, false>(tmW, tmX, p, pdl, st);
+        } else {
+            if (stages == 3 || stages == 4) return launch_gemm_tc_t<16, 4, false>(tmW, tmX, p, pdl, st);
         }
     }
     switch (bn) {

@@ -74,6 +74,7 @@ struct GemmTcParams {
     int64_t ld_out;
     float* partial;               // GT_PARTIAL: [splits][B][N_out] f32 (no bias)
     int w_tiled;                  // 1: W is stored tile-major [N_out/128][K/64][128][64] (each TMA box = 16 KB contiguous in HBM)
+    int l2pf;                     // 1: before waiting for the upstream kernel, prefetch into L2 the weight boxes that do not fit the ring
 };
 inline int gemm_tc_bn(int B) { return B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : B <= 128 ? 128 : 256; }
 int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K, bool tiled);

@@ -74,6 +74,10 @@ typedef struct rqb200_block_weights {
     const void *wqkv, *wproj, *w1, *w2;            /* [3E,E] (rows: query|key|value), [E,E], [4E,E], [E,4E]; weight dtype */
     const float *bqkv, *bproj, *b1, *b2;           /* f32 biases */
     const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;    /* f32 */
+    /* Optional (fast tier only, NULL otherwise): LayerNorm folded into the following Linear.  When cqkv / c1 are non-NULL,
+     * wqkv / w1 hold W*diag(ln_w), bqkv / b1 hold W*ln_b + b, and cqkv [3E] / c1 [4E] hold c_n = sum_k bf16(W*diag(ln_w))[n,k], so
+     * that Linear(LayerNorm(x))[n] = rstd*(W'x - mean*c_n) + b'_n with the row statistics applied in the GEMM epilogue. */
+    const float *cqkv, *c1;
 } rqb200_block_weights;
 
 typedef struct rqb200_ar_config {
@@ -159,6 +163,16 @@ int64_t rqb200_vae_last_launches(const rqb200_vae* h);
  *   and |splits| is the split count. */
 int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out,
                        int out_is_bf16, int gelu, float* partial, int N_out, int K, int B, int splits, void* stream);
+
+/* rqb200_dbg_gemm_gr: one launch of the same GEMM in its "group reduce" form (split-K reduced inside the kernel through an fp32
+ * scratch [N_out/128][splits][B][128] and one arrival counter per 128-feature tile; needs (N_out/128)*splits <= SM count).
+ * kind 0: out f32 [B,N_out] = sum + bias + residual, optional bf16 copy (out_bf16) and per-tile LayerNorm statistics
+ * stats_out [B][N_out/128][2] = (sum, M2 about the tile mean); kind 1: out bf16 = gelu(sum + bias).  stats_in / fold_c (both or
+ * neither): W holds W*diag(gamma), bias holds W*beta + b, fold_c[n] = sum_k W'[n,k] and stats_in [B][K/128][2] are the tile
+ * statistics of the raw input rows: out = act(rstd_b*(sum - mean_b*fold_c[n]) + bias[n]). */
+int rqb200_dbg_gemm_gr(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out, int kind,
+                       float* scratch, unsigned* counters, void* out_bf16, float* stats_out, const float* stats_in,
+                       const float* fold_c, int N_out, int K, int B, int splits, void* stream);
 
 /* rqb200_dbg_conv_tc: one launch of the tcgen05 implicit-GEMM conv (csrc/conv_tc.cu): X NHWC fp16 [B,H,W,Cin], W OHWI fp16
  * [Cout,ks,ks,Cin], stride 1 "same" padding, out f32 NHWC (+bias, +residual) or NCHW when out_nchw.  X16lo / W16lo

@@ -145,7 +145,8 @@ constexpr int AF_MAXT = 512;
 __global__ void __launch_bounds__(128)
 attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, __nv_bfloat16* __restrict__ kc,
                  __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ att, int B, int E, int nh, int Tmax,
-                 const int* __restrict__ t_ptr, int t_host) {
+                 const int* __restrict__ t_ptr, int t_host, const float2* __restrict__ stats_in, int nst,
+                 const float* __restrict__ cqkv) {
     __shared__ float qs[4][64];
     __shared__ float ps[4][AF_MAXT];
     tc::pdl_launch_dependents();
@@ -156,9 +157,12 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     const int b = bh / nh, h = bh % nh;
     const int t = t_ptr ? *t_ptr : t_host;
     const int c = h * 64 + 2 * lane;
-    float2 q = make_float2(bqkv[c], bqkv[c + 1]);
-    float2 k = make_float2(bqkv[E + c], bqkv[E + c + 1]);
-    float2 v = make_float2(bqkv[2 * E + c], bqkv[2 * E + c + 1]);
+    // stats_in != NULL: the qkv GEMM ran on the raw residual rows with LayerNorm folded into its weights (rqb200_block_weights
+    // .cqkv); the row statistics are applied here: q = rstd*(sum - mean*c) + b'
+    const bool fold = stats_in != nullptr;
+    float2 q = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[c], bqkv[c + 1]);
+    float2 k = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[E + c], bqkv[E + c + 1]);
+    float2 v = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[2 * E + c], bqkv[2 * E + c + 1]);
 #pragma unroll 4
     for (int s = 0; s < S; s++) {
         const float* p = part + ((int64_t)s * B + b) * 3 * E;
@@ -166,6 +170,24 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
         float2 bb = *reinterpret_cast<const float2*>(p + E + c);
         float2 cc = *reinterpret_cast<const float2*>(p + 2 * E + c);
         q.x += a.x; q.y += a.y; k.x += bb.x; k.y += bb.y; v.x += cc.x; v.y += cc.y;
+    }
+    if (fold) {
+        float s1 = 0.f;
+        for (int i = lane; i < nst; i += 32) s1 += stats_in[(int64_t)b * nst + i].x;
+        const float mean = warp_sum(s1) / (float)E;
+        float m2 = 0.f;
+        for (int i = lane; i < nst; i += 32) {
+            const float2 st = stats_in[(int64_t)b * nst + i];
+            const float d = st.x * (1.0f / 128.0f) - mean;
+            m2 += st.y + 128.0f * d * d;
+        }
+        const float rstd = rsqrtf(warp_sum(m2) / (float)E + 1e-5f);
+        q.x = rstd * (q.x - mean * cqkv[c]) + bqkv[c];
+        q.y = rstd * (q.y - mean * cqkv[c + 1]) + bqkv[c + 1];
+        k.x = rstd * (k.x - mean * cqkv[E + c]) + bqkv[E + c];
+        k.y = rstd * (k.y - mean * cqkv[E + c + 1]) + bqkv[E + c + 1];
+        v.x = rstd * (v.x - mean * cqkv[2 * E + c]) + bqkv[2 * E + c];
+        v.y = rstd * (v.y - mean * cqkv[2 * E + c + 1]) + bqkv[2 * E + c + 1];
     }
     __nv_bfloat16* kb = kc + ((int64_t)(b * nh + h) * Tmax) * 64;
     __nv_bfloat16* vb = vc + ((int64_t)(b * nh + h) * Tmax) * 64;
@@ -241,6 +263,39 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     *reinterpret_cast<__nv_bfloat162*>(att + (int64_t)b * E + c) = __floats2bfloat162_rn(o.x * inv, o.y * inv);
 }
 
+// RQB200_GR chain with folded LayerNorm: x_out = x_in (+ extra row); xq = bf16(x_out); stats[b][tile] = (sum, M2 about the tile
+// mean) for every 128-feature tile -- what the GT_GR epilogue of proj / fc2 emits for all later layers.  One CTA per batch row,
+// warp <-> tile, lane <-> 4 features.
+__global__ void __launch_bounds__(384)
+row_prep_kernel(const float* __restrict__ x_in, const float* __restrict__ extra, float* __restrict__ x_out,
+                __nv_bfloat16* __restrict__ xq, float2* __restrict__ stats, int B, int E) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nt = E / 128;
+    for (int t = warp; t < nt; t += nw) {
+        const int e = t * 128 + 4 * lane;
+        float4 v = *reinterpret_cast<const float4*>(x_in + (int64_t)b * E + e);
+        if (extra) { const float4 a = *reinterpret_cast<const float4*>(extra + e); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+        if (x_out) *reinterpret_cast<float4*>(x_out + (int64_t)b * E + e) = v;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&h0);
+        pk.y = *reinterpret_cast<unsigned*>(&h1);
+        *reinterpret_cast<uint2*>(xq + (int64_t)b * E + e) = pk;
+        const float s1 = warp_sum((v.x + v.y) + (v.z + v.w));
+        const float tm = s1 * (1.0f / 128.0f);
+        const float d0 = v.x - tm, d1 = v.y - tm, d2 = v.z - tm, d3 = v.w - tm;
+        const float m2 = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+        if (lane == 0) stats[(int64_t)b * nt + t] = make_float2(s1, m2);
+    }
+}
+// arrival counters of the GT_GR GEMMs of one graph: zeroed by the graph's last-but-one kernel for its next replay
+__global__ void __launch_bounds__(256) ctr_zero_kernel(unsigned* __restrict__ ctr, int n) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    for (int i = threadIdx.x; i < n; i += 256) ctr[i] = 0u;
+}
+
 // token sources --------------------------------------------------------------------------------------------------
 // cond token s: x[b,:] = cond_emb[cond[b,s]] + pos_emb_cond[s]                      (transformers.py:224)
 __global__ void __launch_bounds__(256)
@@ -306,7 +361,7 @@ struct ArFast {
     // per (workspace, B) state
     void* ws_base = nullptr;
     int B = 0;
-    CUtensorMap tx_xn, tx_att, tx_h, tx_s;
+    CUtensorMap tx_xn, tx_att, tx_h, tx_s, tx_xq;
     cudaGraphExec_t g_cond = nullptr, g_code = nullptr, g_head = nullptr;
     int64_t n_nodes[3] = {0, 0, 0};      // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
@@ -321,6 +376,11 @@ struct ArFast {
     bool cluster = false;        // all of proj/fc1/fc2 (measured slower than split-K partials + fused LN reduction: 289 vs 243 ms)
     bool fc1_cluster = false;    // fc1 only (RQB200_FC1_CLUSTER=2|3|4): also slower (311-319 ms) -- cluster launches cost more than they save here
     int cl_proj = 8, cl_fc1 = 2, cl_fc2 = 8;
+    // RQB200_GR=1 (experiment for the next round): proj / fc1 / fc2 reduce their split-K partials inside the GEMM (GT_GR), so a block
+    // is ln, qkv, attn, proj, ln, fc1, fc2 (7 launches); with LayerNorm folded into the weights (rqb200_block_weights.cqkv / .c1)
+    // it is qkv, attn, proj, fc1, fc2 (5 launches).  Needs every GT_GR grid co-resident and the GPU to itself.
+    bool gr = false, fold = false;
+    mutable int ctr_next = 0;    // next free arrival counter while a chain is being recorded
     int n_sm = 148;
     MegaParams prog_cond = {}, prog_code = {}, prog_head[8] = {};
 };
@@ -333,6 +393,11 @@ struct FastWs {
     float *XB, *XH, *P, *LOGITS;
     __nv_bfloat16 *XN, *ATT, *Hh, *S;
     __nv_bfloat16 *kc_body, *vc_body, *kc_head, *vc_head;
+    // RQB200_GR chain
+    unsigned* ctr;               // one arrival counter per output tile of every GT_GR GEMM of a graph
+    int ctr_cap;
+    __nv_bfloat16* XQ;           // bf16 copy of the residual rows (folded LayerNorm: the qkv / fc1 operand)
+    float2* ST;                  // [B][E/128] tile statistics of the residual rows
 };
 
 static int pick_split(int n_tiles, int nkb, int want) {
@@ -360,6 +425,10 @@ static size_t fast_layout(const ArFast& f, int B, void* base, size_t cap, FastWs
     w.ATT = a.take<__nv_bfloat16>(B * E);
     w.Hh = a.take<__nv_bfloat16>(B * 4 * E);
     w.S = a.take<__nv_bfloat16>((int64_t)B * c.code_dim);
+    w.ctr_cap = (int)(std::max<int64_t>(c.n_body, (int64_t)c.D * c.n_head_layers) * (6 * E / 128));
+    w.ctr = a.take<unsigned>(w.ctr_cap);
+    w.XQ = a.take<__nv_bfloat16>(B * E);
+    w.ST = a.take<float2>(B * (E / 128));
     const int64_t per_body = (int64_t)B * c.n_head * Tb * 64, per_head = (int64_t)B * c.n_head * c.D * 64;
     w.kc_body = a.take<__nv_bfloat16>(per_body * c.n_body);
     w.vc_body = a.take<__nv_bfloat16>(per_body * c.n_body);
@@ -380,6 +449,24 @@ static int gemm(const ArFast& f, const CUtensorMap& tw, const CUtensorMap& tx, i
     return launch_gemm_tc(tw, tx, p, f.use_pdl, st);
 }
 
+// split-K GEMM with the in-kernel group reduction (GT_GR).  kind 0: out f32 = sum + bias + residual (+ bf16 copy + tile statistics);
+// kind 1: out bf16 = gelu(sum + bias), optionally with the folded LayerNorm of the input rows (stats_in, fold_c).
+static int gemm_gr(const ArFast& f, FastWs& ws, const CUtensorMap& tw, const CUtensorMap& tx, int N_out, int K, int B, int splits,
+                   int kind, const float* bias, void* out, int64_t ld_out, const float* residual, void* out_bf16, float2* stats_out,
+                   const float2* stats_in, const float* fold_c, cudaStream_t st) {
+    const int tiles = N_out / 128;
+    if (f.ctr_next + tiles > ws.ctr_cap) return fail(RQB200_EINVAL, "ar fast tier: out of GT_GR arrival counters");
+    GemmTcParams p = {};
+    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits; p.mode = GT_GR;
+    p.bias = bias; p.bias_scale = 1.f; p.out = out; p.ld_out = ld_out;
+    p.residual = residual; p.ld_res = ld_out;
+    p.w_tiled = f.w_tiled ? 1 : 0;
+    p.gr_scratch = ws.P; p.gr_counter = ws.ctr + f.ctr_next; p.gr_kind = kind;
+    p.gr_out_bf16 = out_bf16; p.gr_stats_out = stats_out; p.gr_stats_in = stats_in; p.gr_fold_c = fold_c;
+    f.ctr_next += tiles;
+    return launch_gemm_tc(tw, tx, p, f.use_pdl, st);
+}
+
 // one transformer stack on the single new token of every batch row; x lives in `x` (fp32), residual additions are
 // deferred into the next ln_reduce.  On return the LAST block's fc2 partials (+ its bias) are still pending.
 static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& blocks, const std::vector<FastLayer>& maps,
@@ -391,6 +478,42 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
     const int64_t per = (int64_t)B * c.n_head * Tmax * 64;
     for (size_t l = 0; l < blocks.size(); l++) {
         const rqb200_block_weights& bw = blocks[l];
+        if (f.gr) {
+            // ---- group-reduce form: x is final after proj / fc2; nothing is ever pending
+            const bool first = l == 0;
+            const bool need_copy = first && (x_src != x || pending_extra != nullptr);
+            const int nt = E / 128;
+            if (f.fold) {
+                if (first)
+                    RQB_TRY(launch_pdl(row_prep_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x_src,
+                                       (const float*)pending_extra, (float*)(need_copy ? x : nullptr), ws.XQ, ws.ST, B, E));
+                RQB_TRY(gemm(f, maps[l].qkv, f.tx_xq, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+                             nullptr, 0, st));
+                RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
+                                   (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
+                                   c.n_head, Tmax, t_ptr, t_host, (const float2*)ws.ST, nt, (const float*)bw.cqkv));
+            } else {
+                RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)(first ? x_src : x),
+                                   (const float*)nullptr, 0, (const float*)nullptr, (const float*)(first ? pending_extra : nullptr),
+                                   (float*)(need_copy ? x : nullptr), (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
+                RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+                             nullptr, 0, st));
+                RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
+                                   (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
+                                   c.n_head, Tmax, t_ptr, t_host, (const float2*)nullptr, 0, (const float*)nullptr));
+            }
+            RQB_TRY(gemm_gr(f, ws, maps[l].proj, f.tx_att, E, E, B, f.split_proj, 0, bw.bproj, x, E, x, f.fold ? ws.XQ : nullptr,
+                            f.fold ? ws.ST : nullptr, nullptr, nullptr, st));
+            if (!f.fold)
+                RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x,
+                                   (const float*)nullptr, 0, (const float*)nullptr, (const float*)nullptr, (float*)nullptr,
+                                   (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
+            RQB_TRY(gemm_gr(f, ws, maps[l].fc1, f.fold ? f.tx_xq : f.tx_xn, 4 * E, E, B, f.split_fc1, 1, bw.b1, ws.Hh, 4 * E, nullptr,
+                            nullptr, nullptr, f.fold ? ws.ST : nullptr, f.fold ? bw.c1 : nullptr, st));
+            RQB_TRY(gemm_gr(f, ws, maps[l].fc2, f.tx_h, E, 4 * E, B, f.split_fc2, 0, bw.b2, x, E, x, f.fold ? ws.XQ : nullptr,
+                            f.fold ? ws.ST : nullptr, nullptr, nullptr, st));
+            continue;
+        }
         if (f.cluster) {
             // ---- cluster split-K form: 6 kernels per block, no partial buffers except for qkv
             const bool first = l == 0;
@@ -402,7 +525,7 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
                          nullptr, 0, st));
             RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
                                (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
-                               c.n_head, Tmax, t_ptr, t_host));
+                               c.n_head, Tmax, t_ptr, t_host, (const float2*)nullptr, 0, (const float*)nullptr));
             RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.cl_proj, GT_F32, bw.bproj, 1.f, x, nullptr, x, E, nullptr, 0, st));
             RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x,
                                (const float*)nullptr, 0, (const float*)nullptr, (const float*)nullptr, (float*)nullptr,
@@ -423,7 +546,7 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
                      nullptr, 0, st));
         if (!(f.skip & 4)) RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
                            (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
-                           c.n_head, Tmax, t_ptr, t_host));
+                           c.n_head, Tmax, t_ptr, t_host, (const float2*)nullptr, 0, (const float*)nullptr));
         if (!(f.skip & 8)) RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
                      nullptr, 0, st));
         if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x,
@@ -555,6 +678,7 @@ static int record_body(ArFast& f, FastWs& ws, bool cond_token, cudaStream_t st) 
         RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, false, ws.state, 1, 0, 0));
         return 0;
     }
+    f.ctr_next = 0;
     if (cond_token) {
         RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B), dim3(256), 0, st, f.use_pdl, (const StepState*)ws.state, w.cond_emb,
                            w.pos_emb_cond, c.cond_len, c.vocab_cond, E, ws.XB));
@@ -567,6 +691,7 @@ static int record_body(ArFast& f, FastWs& ws, bool cond_token, cudaStream_t st) 
     }
     RQB_TRY(fast_stack(f, f.body, f.lbody, ws, ws.XB, false, nullptr, nullptr, ws.XB, ws.kc_body, ws.vc_body, Tb, &ws.state->s,
                        0, st));
+    if (f.gr) RQB_TRY(launch_pdl(ctr_zero_kernel, dim3(1), dim3(256), 0, st, f.use_pdl, ws.ctr, f.ctr_next));
     RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, f.use_pdl, ws.state, 1, 0, 0));
     return 0;
 }
@@ -585,6 +710,7 @@ static int record_head(ArFast& f, FastWs& ws, cudaStream_t st) {
         RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, false, ws.state, 0, 1, D));
         return 0;
     }
+    f.ctr_next = 0;
     for (int d = 0; d < D; d++) {
         if (d == 0) {
             // spatial ctx = body x + pending fc2 of the last body block ; token = ctx + pos_emb_d[0]  (transformers.py:259-270)
@@ -600,14 +726,15 @@ static int record_head(ArFast& f, FastWs& ws, cudaStream_t st) {
         }
         // classifier: LN(x + pending fc2) -> logits                                              (transformers.py:278-285)
         RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)ws.XH,
-                           (const float*)(f.cluster ? nullptr : ws.P), f.cluster ? 0 : f.split_fc2,
-                           (const float*)(f.cluster ? nullptr : f.head.back().b2), (const float*)nullptr, (float*)nullptr, w.cls_ln_w,
+                           (const float*)((f.cluster || f.gr) ? nullptr : ws.P), (f.cluster || f.gr) ? 0 : f.split_fc2,
+                           (const float*)((f.cluster || f.gr) ? nullptr : f.head.back().b2), (const float*)nullptr, (float*)nullptr, w.cls_ln_w,
                            w.cls_ln_b, ws.XN, B, E));
         RQB_TRY(gemm(f, f.tm_cls, f.tx_xn, V, E, B, 1, GT_F32, w.b_cls, 1.f, ws.LOGITS, nullptr, nullptr, 0, nullptr, 0, st));
         RQB_TRY(launch_pdl(logits_copy_kernel, dim3(64), dim3(256), 0, st, f.use_pdl, (const StepState*)ws.state,
                            (const float*)ws.LOGITS, d, (int64_t)B * V));
         RQB_TRY(launch_sample_dyn(ws.LOGITS, ws.state, d, B, V, HW, D, st, f.use_pdl));
     }
+    if (f.gr) RQB_TRY(launch_pdl(ctr_zero_kernel, dim3(1), dim3(256), 0, st, f.use_pdl, ws.ctr, f.ctr_next));
     RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, f.use_pdl, ws.state, 0, 1, D));
     return 0;
 }
@@ -670,6 +797,25 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     f->split_proj = pick_split(E / 128, nkbE, getenv("RQB200_SPLIT_PROJ") ? atoi(getenv("RQB200_SPLIT_PROJ")) : 0);
     f->split_fc1 = pick_split(4 * E / 128, nkbE, getenv("RQB200_SPLIT_FC1") ? atoi(getenv("RQB200_SPLIT_FC1")) : 0);
     f->split_fc2 = pick_split(E / 128, 4 * nkbE, getenv("RQB200_SPLIT_FC2") ? atoi(getenv("RQB200_SPLIT_FC2")) : 0);
+    {
+        bool all_fold = true, any_fold = false;
+        for (const auto& b : body) { all_fold &= (b.cqkv && b.c1); any_fold |= (b.cqkv || b.c1); }
+        for (const auto& b : head) { all_fold &= (b.cqkv && b.c1); any_fold |= (b.cqkv || b.c1); }
+        if ((e = getenv("RQB200_GR")) && e[0] == '1') f->gr = true;
+        // every CTA of a GT_GR grid spins for its tile's peers: the whole grid has to be resident (one CTA per SM)
+        const int g_max = std::max(std::max(E / 128 * f->split_proj, 4 * E / 128 * f->split_fc1), E / 128 * f->split_fc2);
+        if (f->gr && (g_max > f->n_sm || f->cluster || f->want_mega || E % 128 != 0)) {
+            fprintf(stderr, "rqb200: RQB200_GR ignored (a GEMM grid of %d CTAs would not be co-resident on %d SMs, or another chain form is selected)\n",
+                    g_max, f->n_sm);
+            f->gr = false;
+        }
+        f->fold = f->gr && all_fold;
+        if (any_fold && !f->fold) {
+            set_error("ar fast tier: LayerNorm-folded weights (rqb200_block_weights.cqkv / .c1) need the RQB200_GR=1 chain and must be given for every block");
+            delete f;
+            return nullptr;
+        }
+    }
     auto mk = [&](const std::vector<rqb200_block_weights>& bl, std::vector<FastLayer>& out) -> int {
         out.resize(bl.size());
         for (size_t l = 0; l < bl.size(); l++) {
@@ -721,6 +867,7 @@ int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B
         RQB_TRY(make_tmap_2d(&f->tx_att, ws.ATT, 1, E, B, (uint64_t)E * 2, 64, bn));
         RQB_TRY(make_tmap_2d(&f->tx_h, ws.Hh, 1, 4 * E, B, (uint64_t)E * 8, 64, bn));
         RQB_TRY(make_tmap_2d(&f->tx_s, ws.S, 1, c.code_dim, B, (uint64_t)c.code_dim * 2, 64, bn));
+        RQB_TRY(make_tmap_2d(&f->tx_xq, ws.XQ, 1, E, B, (uint64_t)E * 2, 64, bn));
         f->use_mega = f->want_mega && B <= 64 && E <= 224 * 4 * 3 && mega_smem_bytes(E) <= 227 * 1024;
         if (f->use_mega) RQB_TRY(build_programs(*f, ws));
     }
@@ -730,6 +877,7 @@ int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B
     h.temperature = temperature;
     for (int d = 0; d < D; d++) { h.top_k[d] = top_k[d]; h.top_p[d] = top_p[d]; }
     RQB_TRY(launch_pdl(init_state_kernel, dim3(1), dim3(32), 0, st, false, ws.state, h));
+    if (f->gr) RQB_CUDA(cudaMemsetAsync(ws.ctr, 0, (size_t)ws.ctr_cap * sizeof(unsigned), st));
     auto run = [&](int which, cudaGraphExec_t* g) -> int {
         if (!f->use_graph) return which == 0 ? record_body(*f, ws, true, st) : which == 1 ? record_body(*f, ws, false, st)
                                                                                         : record_head(*f, ws, st);

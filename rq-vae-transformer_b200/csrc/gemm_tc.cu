@@ -93,7 +93,106 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
     return v;
 }
 
-template <int BN, int STAGES, bool CL>
+// ---- GT_GR tail, executed by the 128 epilogue threads (warps 2..5; `ew` = 0..3) after they have stored their partial tile.
+__device__ __forceinline__ unsigned gr_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void gr_bar_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float gr_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __noinline__ void gr_reduce_tail(const GemmTcParams& p, int tile, int split, int ew, int lane) {
+    const int S = p.splits;
+    // 1. publish this CTA's partial tile, wait for the S - 1 peers of the tile
+    __threadfence();
+    gr_bar_epilogue();
+    if (ew == 0 && lane == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.gr_counter + tile), "r"(1u) : "memory");
+        const long long t0 = clock64();
+        while (gr_ld_acquire(p.gr_counter + tile) < (unsigned)S) {
+            if (clock64() - t0 > (1ll << 32)) __trap();      // > 2 s: the grid is not co-resident (see GemmTcParams) -- fail, do not hang
+        }
+    }
+    gr_bar_epilogue();
+    // 2. reduce rows [r0, r1) of the tile: warp <-> row (stride 4), lane <-> 4 consecutive output features
+    const int rp = (p.B + S - 1) / S;
+    const int r0 = split * rp, r1 = (r0 + rp) < p.B ? (r0 + rp) : p.B;
+    const float* sc = p.gr_scratch + (int64_t)tile * S * p.B * 128;
+    const int n0 = tile * 128 + 4 * lane;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) {
+        bias4 = *reinterpret_cast<const float4*>(p.bias + n0);
+        bias4.x *= p.bias_scale; bias4.y *= p.bias_scale; bias4.z *= p.bias_scale; bias4.w *= p.bias_scale;
+    }
+    float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.gr_stats_in) c4 = *reinterpret_cast<const float4*>(p.gr_fold_c + n0);
+    const float* res = nullptr;
+    if (p.gr_kind == 0 && p.residual != nullptr) res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0);
+    const int nst = p.K / 128;
+    for (int r = r0 + ew; r < r1; r += 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < S; s0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (s0 + i < S) v[i] = __ldcg(reinterpret_cast<const float4*>(sc + ((int64_t)(s0 + i) * p.B + r) * 128) + lane);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (s0 + i < S) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }   // fixed order
+        }
+        if (p.gr_stats_in) {
+            // LayerNorm statistics of input row r from its per-tile (sum, M2) pairs (Chan's parallel combination)
+            float s1 = 0.f;
+            for (int t = lane; t < nst; t += 32) s1 += p.gr_stats_in[(int64_t)r * nst + t].x;
+            const float mean = gr_warp_sum(s1) / (float)p.K;
+            float m2 = 0.f;
+            for (int t = lane; t < nst; t += 32) {
+                const float2 st = p.gr_stats_in[(int64_t)r * nst + t];
+                const float d = st.x * (1.0f / 128.0f) - mean;
+                m2 += st.y + 128.0f * d * d;
+            }
+            const float rstd = rsqrtf(gr_warp_sum(m2) / (float)p.K + 1e-5f);
+            acc.x = rstd * (acc.x - mean * c4.x); acc.y = rstd * (acc.y - mean * c4.y);
+            acc.z = rstd * (acc.z - mean * c4.z); acc.w = rstd * (acc.w - mean * c4.w);
+        }
+        acc.x += bias4.x; acc.y += bias4.y; acc.z += bias4.z; acc.w += bias4.w;
+        if (p.gr_kind == 1) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(gelu_erf_f(acc.x), gelu_erf_f(acc.y));
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(gelu_erf_f(acc.z), gelu_erf_f(acc.w));
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned*>(&h0);
+            pk.y = *reinterpret_cast<unsigned*>(&h1);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)r * p.ld_out + n0) = pk;
+        } else {
+            if (res) {
+                const float4 rr = *reinterpret_cast<const float4*>(res + (int64_t)r * p.ld_res + n0);
+                acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (int64_t)r * p.ld_out + n0) = acc;
+            if (p.gr_out_bf16) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<unsigned*>(&h0);
+                pk.y = *reinterpret_cast<unsigned*>(&h1);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.gr_out_bf16) + (int64_t)r * p.ld_out + n0) = pk;
+            }
+            if (p.gr_stats_out) {
+                const float s1 = gr_warp_sum((acc.x + acc.y) + (acc.z + acc.w));
+                const float tm = s1 * (1.0f / 128.0f);
+                const float d0 = acc.x - tm, d1 = acc.y - tm, d2 = acc.z - tm, d3 = acc.w - tm;
+                const float m2 = gr_warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+                if (lane == 0) p.gr_stats_out[(int64_t)r * (p.N_out / 128) + tile] = make_float2(s1, m2);
+            }
+        }
+    }
+}
+
+template <int BN, int STAGES, bool CL, bool GR = false>
 __global__ void __launch_bounds__(GT_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, GemmTcParams p) {
     constexpr int B_BYTES = BN * 64 * 2;
@@ -188,7 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 for (int i = 0; i < 16; i++) stg[(q * 32 + lane) * (BN + 1) + c0 + i] = __uint_as_float(r[i]);
             }
         } else {
-        const float bias = (p.bias != nullptr && nvalid && p.mode != GT_PARTIAL) ? p.bias[n] * p.bias_scale : 0.f;
+        const float bias = (p.bias != nullptr && nvalid && p.mode != GT_PARTIAL && !GR) ? p.bias[n] * p.bias_scale : 0.f;
         const float* res = nullptr;
         if (p.mode == GT_F32 && p.residual != nullptr)
             res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0);
@@ -224,10 +323,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     case GT_PARTIAL:
                         p.partial[((int64_t)split * p.B + b) * p.N_out + n] = v;
                         break;
+                    case GT_GR:
+                        if (GR) __stcg(p.gr_scratch + (((int64_t)tile * p.splits + split) * p.B + b) * 128 + (q * 32 + lane), v);
+                        break;
                 }
             }
             }
         }
+        if constexpr (GR) gr_reduce_tail(p, tile, split, warp - 2, lane);
         }
     }
     if (CL) {
@@ -273,13 +376,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES, bool CL>
+template <int BN, int STAGES, bool CL, bool GR = false>
 static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (GT_A_BYTES + BN * 128) + 1024 + 256;
     static_assert(!CL || (size_t)STAGES * (GT_A_BYTES + BN * 128) >= (size_t)128 * (BN + 1) * 4, "staging area must fit in the ring");
     static bool attr = false;
     if (!attr) {
-        RQB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RQB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CL, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -299,7 +402,7 @@ static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, cons
         at[1].val.clusterDim.z = 1;
         cfg.numAttrs = 2;
     }
-    RQB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, CL>, tmW, tmX, p));
+    RQB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, CL, GR>, tmW, tmX, p));
     g_launches++;
     return 0;
 }
@@ -311,6 +414,17 @@ int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcP
     if (p.B < 1 || p.B > 256) return fail(RQB200_EINVAL, "gemm_tc: batch rows must be in [1,256]");
     if (p.splits < 1 || p.splits > p.K / 64) return fail(RQB200_EINVAL, "gemm_tc: bad split count");
     const int bn = gemm_tc_bn(p.B);
+    if (p.mode == GT_GR && (p.gr_scratch == nullptr || p.gr_counter == nullptr || p.ld_out % 4 != 0 || (p.gr_stats_in && p.K % 128 != 0)))
+        return fail(RQB200_EINVAL, "gemm_tc: GT_GR needs scratch, counters, ld_out % 4 == 0 (and K % 128 == 0 with a folded LayerNorm)");
+    if (p.mode == GT_GR) {
+        switch (bn) {
+            case 16: return launch_gemm_tc_t<16, 8, false, true>(tmW, tmX, p, pdl, st);
+            case 32: return launch_gemm_tc_t<32, 8, false, true>(tmW, tmX, p, pdl, st);
+            case 64: return launch_gemm_tc_t<64, 8, false, true>(tmW, tmX, p, pdl, st);
+            case 128: return launch_gemm_tc_t<128, 6, false, true>(tmW, tmX, p, pdl, st);
+            default: return launch_gemm_tc_t<256, 4, false, true>(tmW, tmX, p, pdl, st);
+        }
+    }
     if (p.splits > 1 && p.mode != GT_PARTIAL) {          // split-K with an in-kernel (cluster / DSMEM) reduction
         if (p.splits > 8) return fail(RQB200_EINVAL, "gemm_tc: cluster split-K supports at most 8 splits");
         switch (bn) {
@@ -371,5 +485,28 @@ extern "C" int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const 
     p.bias = bias; p.bias_scale = 1.f; p.residual = residual; p.ld_res = N_out; p.out = out; p.ld_out = N_out; p.partial = partial;
     p.w_tiled = tiled ? 1 : 0;
     p.mode = (splits > 1 && partial != nullptr) ? GT_PARTIAL : (out_is_bf16 ? (gelu ? GT_BF16_GELU : GT_BF16) : GT_F32);
+    return launch_gemm_tc(tw, tx, p, false, (cudaStream_t)stream);
+}
+
+// one GT_GR launch (split-K with the in-kernel group reduction); scratch >= splits*B*N_out floats, counters >= N_out/128 (zeroed here)
+extern "C" int rqb200_dbg_gemm_gr(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out, int kind,
+                                  float* scratch, unsigned* counters, void* out_bf16, float* stats_out, const float* stats_in,
+                                  const float* fold_c, int N_out, int K, int B, int splits, void* stream) {
+    using namespace rqb;
+    CUtensorMap tw, tx;
+    const int bn = gemm_tc_bn(B);
+    RQB_TRY(make_tmap_weight(&tw, W_bf16, N_out, K, false));
+    RQB_TRY(make_tmap_2d(&tx, X_bf16, 1, (uint64_t)K, (uint64_t)B, (uint64_t)K * 2, 64, (uint32_t)bn));
+    int dev = 0, n_sm = 0;
+    RQB_CUDA(cudaGetDevice(&dev));
+    RQB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    if ((N_out / 128) * splits > n_sm) return fail(RQB200_EINVAL, "dbg_gemm_gr: the grid would not be co-resident");
+    RQB_CUDA(cudaMemsetAsync(counters, 0, (size_t)(N_out / 128) * sizeof(unsigned), (cudaStream_t)stream));
+    GemmTcParams p = {};
+    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits; p.mode = GT_GR;
+    p.bias = bias; p.bias_scale = 1.f; p.residual = kind == 0 ? residual : nullptr; p.ld_res = N_out; p.out = out; p.ld_out = N_out;
+    p.gr_scratch = scratch; p.gr_counter = counters; p.gr_kind = kind; p.gr_out_bf16 = out_bf16;
+    p.gr_stats_out = reinterpret_cast<float2*>(stats_out); p.gr_stats_in = reinterpret_cast<const float2*>(stats_in);
+    p.gr_fold_c = fold_c;
     return launch_gemm_tc(tw, tx, p, false, (cudaStream_t)stream);
 }

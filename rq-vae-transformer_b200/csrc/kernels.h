@@ -60,7 +60,7 @@ int make_tmap_4d_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W
                       uint32_t box_w, uint32_t box_h, uint32_t box_b);
 
 // gemm_tc.cu -- tcgen05 weight-streaming GEMM (fast tier)
-enum GemmTcMode { GT_F32 = 0, GT_BF16 = 1, GT_BF16_GELU = 2, GT_PARTIAL = 3 };
+enum GemmTcMode { GT_F32 = 0, GT_BF16 = 1, GT_BF16_GELU = 2, GT_PARTIAL = 3, GT_GR = 4 };
 struct GemmTcParams {
     int N_out, K, B, splits, mode;
     const float* bias;            // [N_out] (nullable); added as bias * bias_scale
@@ -75,6 +75,18 @@ struct GemmTcParams {
     float* partial;               // GT_PARTIAL: [splits][B][N_out] f32 (no bias)
     int w_tiled;                  // 1: W is stored tile-major [N_out/128][K/64][128][64] (each TMA box = 16 KB contiguous in HBM)
     int l2pf;                     // 1: before waiting for the upstream kernel, prefetch into L2 the weight boxes that do not fit the ring
+    // GT_GR ("group reduce"): split-K whose reduction happens INSIDE the kernel.  Every split CTA stores its fp32 partial tile to
+    // gr_scratch (stays in L2), signals the tile's arrival counter, waits for its `splits` peers and then reduces its own slice of
+    // the batch rows in a fixed split order (deterministic) and applies the epilogue -- no separate reduction launch.
+    // All CTAs of the grid must be co-resident (grid <= SMs x occupancy) and no other spinning grid may share the GPU.
+    float* gr_scratch;            // [N_out/128][splits][B][128] f32
+    unsigned* gr_counter;         // [N_out/128], zero before the launch
+    int gr_kind;                  // 0: out f32 [B,ld_out] = sum + bias + residual (+ gr_out_bf16, + gr_stats_out); 1: out bf16 = gelu(sum + bias)
+    void* gr_out_bf16;            // kind 0, nullable: bf16 copy of the new rows [B, ld_out]
+    float2* gr_stats_out;         // kind 0, nullable: [B][N_out/128] (sum, M2 about the tile mean) of the new rows -- LayerNorm statistics
+    // folded LayerNorm on the INPUT rows (weights hold W*diag(gamma), bias holds W*beta + b): v = rstd_b*(sum - mean_b*c_n) + bias_n
+    const float2* gr_stats_in;    // [B][K/128] tile statistics of the input rows, NULL: no fold
+    const float* gr_fold_c;       // [N_out]  c_n = sum_k W'[n,k]
 };
 inline int gemm_tc_bn(int B) { return B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : B <= 128 ? 128 : 256; }
 int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K, bool tiled);

@@ -162,14 +162,30 @@ class RQTransformer(Stage2Model):
             keep.append(t)
             return t.data_ptr()
 
+        # experiment (fast tier, RQB200_LNFOLD=1, used by the RQB200_GR=1 chain): fold each LayerNorm into the Linear after it,
+        # Linear(LN(x))[n] = rstd*(W'x - mean*c_n) + b'_n with W' = W*diag(gamma), b' = W*beta + b, c_n = sum_k bf16(W')[n,k]
+        lnfold = (mode == N.MODE_FAST and os.environ.get("RQB200_LNFOLD", "0") == "1"
+                  and os.environ.get("RQB200_GR", "0") == "1")
+
+        def folded(W, bias, ln):
+            W, bias = W.detach().float(), bias.detach().float()
+            Wf = W * ln.weight.detach().float()[None, :]
+            c = Wf.to(torch.bfloat16).float().sum(1)
+            return wt(Wf), f32(W @ ln.bias.detach().float() + bias), f32(c)
+
         def blocks(stack):
             arr = (N.BlockWeights * len(stack.blocks))()
             for i, b in enumerate(stack.blocks):
                 a = b.attn
-                arr[i].wqkv = wt(torch.cat([a.query.weight, a.key.weight, a.value.weight], 0))
-                arr[i].bqkv = f32(torch.cat([a.query.bias, a.key.bias, a.value.bias], 0))
+                wqkv = torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)
+                bqkv = torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)
+                if lnfold:
+                    arr[i].wqkv, arr[i].bqkv, arr[i].cqkv = folded(wqkv, bqkv, b.ln1)
+                    arr[i].w1, arr[i].b1, arr[i].c1 = folded(b.mlp[0].weight, b.mlp[0].bias, b.ln2)
+                else:
+                    arr[i].wqkv, arr[i].bqkv = wt(wqkv), f32(bqkv)
+                    arr[i].w1, arr[i].b1 = wt(b.mlp[0].weight), f32(b.mlp[0].bias)
                 arr[i].wproj, arr[i].bproj = wt(a.proj.weight), f32(a.proj.bias)
-                arr[i].w1, arr[i].b1 = wt(b.mlp[0].weight), f32(b.mlp[0].bias)
                 arr[i].w2, arr[i].b2 = wt(b.mlp[2].weight), f32(b.mlp[2].bias)
                 arr[i].ln1_w, arr[i].ln1_b = f32(b.ln1.weight), f32(b.ln1.bias)
                 arr[i].ln2_w, arr[i].ln2_b = f32(b.ln2.weight), f32(b.ln2.bias)
@@ -256,6 +272,8 @@ class RQTransformer(Stage2Model):
         if mode == N.MODE_FAST and not return_logits and force_codes is None:
             n_streams = int(os.environ.get("RQB200_AR_STREAMS", "1"))
             n_streams = max(1, min(n_streams, B // 8 if B >= 8 else 1))
+            if os.environ.get("RQB200_GR", "0") == "1":
+                n_streams = 1        # GT_GR grids spin for their peers: two of them on one GPU could wait for each other forever
         with torch.cuda.device(dev):
             if noise is None:
                 # one exponential_ per token, in (h,w,d) order: the draws torch.multinomial would make (utils.py:114)

@@ -173,11 +173,11 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     }
     if (fold) {
         float s1 = 0.f;
-        for (int i = lane; i < nst; i += 32) s1 += stats_in[(int64_t)b * nst + i].x;
+        for (int i = lane; i < nst; i += 32) s1 += __ldcg(stats_in + (int64_t)b * nst + i).x;
         const float mean = warp_sum(s1) / (float)E;
         float m2 = 0.f;
         for (int i = lane; i < nst; i += 32) {
-            const float2 st = stats_in[(int64_t)b * nst + i];
+            const float2 st = __ldcg(stats_in + (int64_t)b * nst + i);
             const float d = st.x * (1.0f / 128.0f) - mean;
             m2 += st.y + 128.0f * d * d;
         }

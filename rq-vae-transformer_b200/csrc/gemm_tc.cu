@@ -148,11 +148,11 @@ __device__ __noinline__ void gr_reduce_tail(const GemmTcParams& p, int tile, int
         if (p.gr_stats_in) {
             // LayerNorm statistics of input row r from its per-tile (sum, M2) pairs (Chan's parallel combination)
             float s1 = 0.f;
-            for (int t = lane; t < nst; t += 32) s1 += p.gr_stats_in[(int64_t)r * nst + t].x;
+            for (int t = lane; t < nst; t += 32) s1 += __ldcg(p.gr_stats_in + (int64_t)r * nst + t).x;
             const float mean = gr_warp_sum(s1) / (float)p.K;
             float m2 = 0.f;
             for (int t = lane; t < nst; t += 32) {
-                const float2 st = p.gr_stats_in[(int64_t)r * nst + t];
+                const float2 st = __ldcg(p.gr_stats_in + (int64_t)r * nst + t);
                 const float d = st.x * (1.0f / 128.0f) - mean;
                 m2 += st.y + 128.0f * d * d;
             }
@@ -170,7 +170,7 @@ __device__ __noinline__ void gr_reduce_tail(const GemmTcParams& p, int tile, int
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)r * p.ld_out + n0) = pk;
         } else {
             if (res) {
-                const float4 rr = *reinterpret_cast<const float4*>(res + (int64_t)r * p.ld_res + n0);
+                const float4 rr = __ldcg(reinterpret_cast<const float4*>(res + (int64_t)r * p.ld_res + n0));
                 acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w;
             }
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (int64_t)r * p.ld_out + n0) = acc;

@@ -8,6 +8,10 @@ namespace rqb {
 // rq_search.cu
 int launch_rq_quantize(const float* x, const float* cb, int64_t N, int K, int C, int D, int64_t* codes, float* quant_list,
                        float* resid_out, cudaStream_t st);
+// rq_search2.cu -- 8x8 register tile, codebook streamed in 32-channel slabs, 2-CTA clusters splitting the codebook (RQB200_RQ_V2=1)
+bool rq_quantize2_supported(int64_t N, int K, int C);
+int launch_rq_quantize2(const float* x, const float* cb, int64_t N, int K, int C, int D, int64_t* codes, float* quant_list,
+                        float* resid_out, cudaStream_t st);
 int launch_rq_embed(const int64_t* codes, const float* cb, int64_t N, int D, int K, int C, float* out, bool sum,
                     cudaStream_t st);
 // sampler.cu

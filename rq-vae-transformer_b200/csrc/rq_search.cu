@@ -15,7 +15,9 @@
 // as the reference forms them; argmin keeps the first index on ties (strict < inside a thread visiting k in
 // increasing order, (dist,idx)-lexicographic shuffles across threads).  Bound: FP32 FFMA (2*N*K*C*D flop), not HBM
 // (SURVEY.md finding 4); the HBM figure is reported as well because the north star asks for it.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "kernels.h"
 
 namespace rqb {
 
@@ -249,6 +251,9 @@ int launch_rq_quantize(const float* x, const float* cb, int64_t N, int K, int C,
     if (C != RQ_C) return fail(RQB200_EINVAL, "rq_quantize: C must be 256");
     if (N < 0 || K <= 0 || D <= 0) return fail(RQB200_EINVAL, "rq_quantize: bad shape");
     if (N == 0) return 0;   // empty input: nothing to do (reference returns empty tensors)
+    // experiment for the next round (csrc/rq_search2.cu): same arithmetic, 8x8 register tile, 2-CTA clusters splitting the codebook
+    if (const char* e = getenv("RQB200_RQ_V2"))
+        if (e[0] == '1' && rq_quantize2_supported(N, K, C)) return launch_rq_quantize2(x, cb, N, K, C, D, codes, quant_list, resid_out, st);
     static bool attr_set = false;
     if (!attr_set) {
         RQB_CUDA(cudaFuncSetAttribute(rq_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RqSmem)));

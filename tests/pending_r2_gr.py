@@ -144,3 +144,35 @@ def test_gr_chain_free_running_consistency(golden, layouts, env):
         d = _with_env(model, dict(env, **{var: "1"}),
                       lambda: model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=noise))
         assert torch.equal(a, d), var
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# P1: second form of the fused RQ search (csrc/rq_search2.cu, RQB200_RQ_V2=1).  Same arithmetic operation for operation, so the
+# first kernel -- pinned to the reference's golden vectors in tests/test_gpu_parity.py -- is its oracle, bit for bit.
+@pytest.mark.parametrize("n,K", [(128, 2048), (4096, 16384), (100, 1000), (64, 256), (1, 300), (200, 16384), (65, 257), (4096, 2048)])
+def test_rq_search_v2_bit_identical_to_v1(n, K):
+    from rqvae import _native as N
+    from rqvae.models import _bind as nb
+    x = (synth.randn_seeded((n, 256), 11) * 0.2).to(DEV)
+    cb = synth.randn_seeded((K, 256), 12).to(DEV)
+    D = 4
+
+    def run(v2):
+        if v2:
+            os.environ["RQB200_RQ_V2"] = "1"
+        try:
+            ql, codes = nb.rq_quantize(x, cb, D, want_list=True)
+            res = torch.empty_like(x)
+            codes2 = torch.empty_like(codes)
+            N.check(N.lib().rqb200_rq_quantize(N.ptr(x), N.ptr(cb), n, K, 256, D, N.ptr(codes2), None, N.ptr(res), None), "rq")
+            torch.cuda.synchronize()
+            return ql, codes, codes2, res
+        finally:
+            os.environ.pop("RQB200_RQ_V2", None)
+
+    ql1, c1, c1b, r1 = run(False)
+    ql2, c2, c2b, r2 = run(True)
+    assert torch.equal(c1, c2) and torch.equal(c1b, c2b), "codes differ: %d" % int((c1 != c2).sum())
+    assert torch.equal(ql1, ql2), "aggregates differ"
+    assert torch.equal(r1, r2), "residuals differ"
+    assert torch.equal(c1, c1b)

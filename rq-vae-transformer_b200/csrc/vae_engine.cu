@@ -24,6 +24,7 @@ struct rqb200_vae {
     bool finalized = false;
     bool fast_ok = false;     // FAST mode and every decoder channel count is a multiple of 128
     bool split = false;       // split-fp16 (3 products per conv): "<key>.weight_lo" tensors registered
+    bool enc_fast = false;    // the encoder's stride-1 convs were registered in fp16 as well (RQB200_ENC_FAST=1): encode on the tcgen05 path
     int64_t last_launches = 0;
     int64_t max_act = 0;      // max H*W*C per image over all activations
     int64_t max_gn_hw = 0;
@@ -223,8 +224,42 @@ struct VaeRun {
         return conv("decoder.conv_out", buf[a], out, nullptr, res, res, ch, c.out_ch, 3, 1, 0, 0, 1);
     }
 
+    // fast-tier encoder (experiment, RQB200_ENC_FAST=1 on the host side registers fp16 hi/lo weights for these layers): every
+    // stride-1 conv on the tcgen05 path through the decoder's building blocks; conv_in (Cin = 3, NCHW input) and the five
+    // stride-2 downsample convs stay on the fp32 FFMA kernel (2 % of the encoder's flops)
+    int encode_fast(const float* x, float* z_e) {
+        const rqb200_vae_config& c = h->cfg;
+        const int nl = c.n_levels, nb = c.num_res_blocks;
+        int res = c.resolution, rc = 0, ch = c.ch, cur = 0;
+        rc = conv("encoder.conv_in", x, buf[0], nullptr, res, res, c.in_channels, ch, 3, 1, 0, 1, 0); if (rc) return rc;
+        for (int lvl = 0; lvl < nl; lvl++) {
+            int cout = c.ch * c.ch_mult[lvl];
+            std::string p = "encoder.down." + std::to_string(lvl);
+            for (int b = 0; b < nb; b++) {
+                cur = resblock_f(p + ".block." + std::to_string(b), cur, res, res, ch, cout, &rc); if (rc) return rc;
+                ch = cout;
+                if (has_attn(res)) { cur = attnblock_f(p + ".attn." + std::to_string(b), cur, res, res, ch, &rc); if (rc) return rc; }
+            }
+            if (lvl != nl - 1) {
+                int nxt = (cur + 1) & 3;
+                rc = conv(p + ".downsample.conv", buf[cur], buf[nxt], nullptr, res, res, ch, ch, 3, 2, 0, 0, 0); if (rc) return rc;
+                cur = nxt;
+                res /= 2;
+            }
+        }
+        cur = resblock_f("encoder.mid.block_1", cur, res, res, ch, ch, &rc); if (rc) return rc;
+        cur = attnblock_f("encoder.mid.attn_1", cur, res, res, ch, &rc); if (rc) return rc;
+        cur = resblock_f("encoder.mid.block_2", cur, res, res, ch, ch, &rc); if (rc) return rc;
+        int b2 = (cur + 2) & 3;
+        rc = gn_f("encoder.norm_out", buf[cur], h16[0], res * res, ch, 1); if (rc) return rc;
+        rc = conv_f("encoder.conv_out", h16[0], buf[b2], nullptr, res, res, ch, c.z_channels, 3, 0); if (rc) return rc;
+        if (!dry) { rc = launch_cast_f16(buf[b2], h16[0], l16[0], B, res, res, c.z_channels, 0, st); if (rc) return rc; }
+        return conv_f("quant_conv", h16[0], z_e, nullptr, res, res, c.z_channels, c.embed_dim, 1, 0);
+    }
+
     // Encoder.forward (modules.py:73-98) followed by quant_conv (rqvae.py:82).  x NCHW -> z_e NHWC.
     int encode(const float* x, float* z_e) {
+        if (fast && h->enc_fast) return encode_fast(x, z_e);
         const rqb200_vae_config& c = h->cfg;
         const int nl = c.n_levels, nb = c.num_res_blocks;
         int res = c.resolution, rc = 0, ch = c.ch, cur = 0;
@@ -319,9 +354,13 @@ int rqb200_vae_finalize(rqb200_vae* h) {
         h->fast_ok = ok;
         h->split = ok && h->t.find("decoder.conv_in.weight_lo") != h->t.end();
     }
+    {
+        auto it = h->t.find("encoder.conv_out.weight");
+        h->enc_fast = h->fast_ok && it != h->t.end() && it->second.dtype == RQB200_F16;
+    }
     run.fast = h->fast_ok;
     run.decode(nullptr, nullptr);
-    run.fast = false;
+    run.fast = h->fast_ok && h->enc_fast;
     run.encode(nullptr, nullptr);
     if (!run.missing.empty()) return rqb::fail(RQB200_ESTATE, "vae_finalize: tensor " + run.missing);
     if (h->t.find("codebook") == h->t.end()) return rqb::fail(RQB200_ESTATE, "vae_finalize: tensor codebook (missing)");
@@ -375,7 +414,7 @@ int rqb200_vae_encode(rqb200_vae* h, const float* x, int B, float* z_e, void* wo
                       void* stream) {
     rqb::VaeRun run;
     RQB_TRY(vae_prepare(h, B, workspace, workspace_bytes, stream, &run));
-    run.fast = false;            // encoder: exact-tier kernels (stride-2 convs / Cin=3 are not on the tcgen05 path yet)
+    run.fast = h->fast_ok && h->enc_fast;   // default: exact-tier kernels for the whole encoder; see encode_fast
     int rc = run.encode(x, z_e);
     h->last_launches = rqb::g_launches;
     return rc;

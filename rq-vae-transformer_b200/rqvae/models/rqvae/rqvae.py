@@ -5,6 +5,7 @@ Boundary kept: ``encode`` :80, ``decode`` :85, ``forward`
 state_dict key layout.  ``precision``: 'exact' = fp32 FFMA kernels, 'fast' = fp16-operand / fp32-accumulate tcgen05
 implicit GEMM (the reference's own GPU decode runs cuDNN with TF32 allowed -- same 10-bit mantissa class)."""
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -85,6 +86,7 @@ class RQVAE(Stage1Model):
         if not handle:
             raise N.NativeError("rqb200_vae_create: " + L.rqb200_last_error().decode())
         wdt = torch.float16 if mode == N.MODE_FAST else torch.float32
+        enc_fast = mode == N.MODE_FAST and os.environ.get("RQB200_ENC_FAST", "0") == "1"
         keep = {}
 
         def reg(name, t):
@@ -95,7 +97,11 @@ class RQVAE(Stage1Model):
         def reg_conv(name, w_oihw):
             """conv weight OIHW -> OHWI in the engine's dtype; fast tier: fp16 hi + lo halves (split-fp16 products)"""
             w = w_oihw.detach().permute(0, 2, 3, 1).contiguous().float()
-            if mode == N.MODE_FAST and name.startswith(("decoder.", "post_quant_conv")):
+            fast16 = name.startswith(("decoder.", "post_quant_conv"))
+            if enc_fast and name.startswith(("encoder.", "quant_conv")) and not name.startswith("encoder.conv_in") \
+                    and ".downsample." not in name:
+                fast16 = True     # experiment (RQB200_ENC_FAST=1): the encoder's stride-1 convs on the tcgen05 path too
+            if mode == N.MODE_FAST and fast16:
                 hi = w.to(torch.float16)
                 reg(name, hi)
                 if self.split_fp16:

@@ -176,3 +176,30 @@ def test_rq_search_v2_bit_identical_to_v1(n, K):
     assert torch.equal(ql1, ql2), "aggregates differ"
     assert torch.equal(r1, r2), "residuals differ"
     assert torch.equal(c1, c1b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# P2: fast-tier encoder (csrc/vae_engine.cu encode_fast, RQB200_ENC_FAST=1): the decoder's tcgen05 building blocks on the
+# encoder's stride-1 convs.  z_e within the pixel-class tolerance of the reference fixture; codes may flip only at near-ties.
+@pytest.mark.parametrize("name", ["ffhq", "imagenet"])
+def test_vae_fast_tier_encode_within_1e3(golden, layouts, name):
+    from oracle.zoo import VAE_ZOO, vae_ddconfig
+    from tests.helpers import build_vae
+    g = golden("vae")["vae"][name]
+    kw = VAE_ZOO[name]
+    R = vae_ddconfig(**kw)["resolution"]
+    os.environ["RQB200_ENC_FAST"] = "1"
+    try:
+        model, sd = build_vae(name, layouts, g["weight_seed"])
+        model.precision = "fast"
+        x = synth.randn_seeded((2, 3, R, R), g["x_seed"]).to(DEV)
+        z_e = model.encode(x).cpu()
+        rel = float((z_e - g["z_e"]).norm() / g["z_e"].norm())
+        print("%s fast encode: rel-L2 %.3e" % (name, rel))
+        assert rel < 1e-3
+        codes = model.get_codes(x).cpu()
+        mism = int((codes.to(torch.int32) != g["codes_fwd"]).sum())
+        print("%s fast encode: %d / %d codes differ from the reference's" % (name, mism, codes.numel()))
+        assert mism <= max(2, codes.numel() // 50)
+    finally:
+        del os.environ["RQB200_ENC_FAST"]

@@ -16,6 +16,8 @@
 //      double accumulator for float), cut after the first position whose cumulative mass >= p, renormalise by the
 //      kept mass.
 //   5. out = argmax_i p_i / q_i, first index on ties.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -23,6 +25,8 @@ namespace rqb {
 
 constexpr int SMP_THREADS = 1024;
 constexpr int SMP_MAXV = 16384;
+constexpr int SMP_NB = 2048;       // buckets of the linear-map select
+constexpr int SMP_MAXC = 1024;     // candidates of the threshold bucket that are ranked exactly; more -> radix select
 
 __device__ __forceinline__ uint32_t f2key(float f) {   // monotone: larger float -> larger key
     uint32_t u = __float_as_uint(f);
@@ -44,7 +48,7 @@ __device__ __forceinline__ bool item_before(const SortItem& a, const SortItem& b
 __global__ void __launch_bounds__(SMP_THREADS, 1)
 sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise, int V, float temperature, int top_k,
               float top_p, int64_t* __restrict__ out_idx, const int64_t* __restrict__ force, int64_t out_stride,
-              const StepState* __restrict__ stt, int dyn_d, int dyn_HW, int dyn_D) {
+              const StepState* __restrict__ stt, int dyn_d, int dyn_HW, int dyn_D, int algo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xs = reinterpret_cast<float*>(smem_raw);                       // [V]   scaled logits, later probabilities
     SortItem* items = reinterpret_cast<SortItem*>(xs + V);                // [Vpad] only touched when top_p < 1
@@ -52,6 +56,10 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise
     __shared__ float red[33];
     __shared__ int redi[33];
     __shared__ unsigned int sel_prefix, sel_remaining, n_surv;
+    __shared__ unsigned int bk_hist[SMP_NB];                // bucket select (algo 1)
+    __shared__ float bk_cand[SMP_MAXC];
+    __shared__ unsigned int bk_ncand, bk_bin, bk_rem, bk_fallback;
+    __shared__ float bk_kth;
     __shared__ double scan_carry[33];
     __shared__ int cut_pos;
     __shared__ float kept_mass;
@@ -82,7 +90,94 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise
     // ---- 2. top-k threshold: exact k-th largest by an 8-pass, 4-bit radix select.  No shared-memory atomics and no
     // MATCH: every thread keeps its <= 16 order-preserving keys in registers, counts the 16 digit values in packed
     // 16-bit lanes (8 words), the warp reduces them with shuffles, one word per thread sums the 32 warps.
-    if (top_k > 0 && top_k < V) {
+    bool kth_done = false;
+    if (algo == 1 && top_k > 0 && top_k < V) {
+        // ---- 2'. bucket select (RQB200_SAMPLER_V2=1): the k-th largest VALUE through one 2048-bucket histogram over the row's
+        // [min, max] range (a monotone linear map, so bucket order == value order), a suffix scan to find the bucket that holds
+        // it, and an exact ranking of that bucket's few members.  Rows with non-finite entries, a degenerate range or an
+        // overfull threshold bucket take the radix select below.  Same threshold value => identical masking.
+        float vals[16];
+        float lo = INFINITY, hi = -INFINITY;
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int i = t + j * SMP_THREADS;
+            vals[j] = 0.f;
+            if (i < V) {
+                const float v = xs[i];
+                vals[j] = v;
+                bad |= !(fabsf(v) <= 3.0e38f);               // NaN or +-inf
+                lo = fminf(lo, v);
+                hi = fmaxf(hi, v);
+            }
+        }
+        for (int i = t; i < SMP_NB; i += SMP_THREADS) bk_hist[i] = 0u;
+        if (t == 0) { bk_ncand = 0u; bk_fallback = 0u; bk_bin = 0u; bk_rem = 0u; }
+        const float gmax = block_max(hi, red);
+        const float gmin = -block_max(-lo, red);
+        const int anybad = __syncthreads_or(bad ? 1 : 0);
+        if (!anybad && gmax > gmin) {                          // block-uniform
+            const float scale = (float)SMP_NB / (gmax - gmin);
+            int bins[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int i = t + j * SMP_THREADS;
+                int b = (int)((vals[j] - gmin) * scale);
+                b = b < 0 ? 0 : (b > SMP_NB - 1 ? SMP_NB - 1 : b);
+                bins[j] = b;
+                if (i < V) atomicAdd(&bk_hist[b], 1u);
+            }
+            __syncthreads();
+            // suffix scan: thread t owns buckets 2t (low) and 2t+1 (high); `above` = members of all buckets above 2t+1
+            const unsigned h0 = bk_hist[2 * t], h1 = bk_hist[2 * t + 1];
+            unsigned incl = h0 + h1;                           // inclusive suffix sum over lanes >= lane
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned dn = __shfl_down_sync(0xffffffffu, incl, o);
+                if (lane + o < 32) incl += dn;
+            }
+            unsigned* wtot = reinterpret_cast<unsigned*>(redi);
+            if (lane == 0) wtot[wid] = incl;                   // this warp's total
+            __syncthreads();
+            unsigned wabove = 0u;                              // members held by warps above this one
+            for (int w = wid + 1; w < SMP_THREADS / 32; w++) wabove += wtot[w];
+            const unsigned above = wabove + incl - (h0 + h1);
+            const unsigned k_u = (unsigned)top_k;
+            if (above < k_u && k_u <= above + h1) { bk_bin = 2u * t + 1u; bk_rem = k_u - above; if (h1 > SMP_MAXC) bk_fallback = 1u; }
+            else if (above + h1 < k_u && k_u <= above + h1 + h0) { bk_bin = 2u * t; bk_rem = k_u - above - h1; if (h0 > SMP_MAXC) bk_fallback = 1u; }
+            __syncthreads();
+            if (!bk_fallback) {                                // block-uniform (written before the barrier)
+                const int bstar = (int)bk_bin;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int i = t + j * SMP_THREADS;
+                    if (i < V && bins[j] == bstar) bk_cand[atomicAdd(&bk_ncand, 1u)] = vals[j];
+                }
+                __syncthreads();
+                const int nc = (int)bk_ncand;
+                const unsigned rem_u = bk_rem;
+                if (t < nc) {
+                    const float v = bk_cand[t];
+                    unsigned gt = 0u, ge = 0u;
+                    for (int i = 0; i < nc; i++) {
+                        const float o2 = bk_cand[i];
+                        gt += o2 > v ? 1u : 0u;
+                        ge += o2 >= v ? 1u : 0u;
+                    }
+                    if (gt < rem_u && rem_u <= ge) bk_kth = v;   // every thread that qualifies holds the same value
+                }
+                __syncthreads();
+                const float kth = bk_kth;
+                for (int i = t; i < V; i += SMP_THREADS) {
+                    float v = xs[i];
+                    if (v < kth) xs[i] = -INFINITY;
+                }
+                __syncthreads();
+                kth_done = true;
+            }
+        }
+    }
+    if (!kth_done && top_k > 0 && top_k < V) {
         uint32_t keys[16];
         uint32_t valid = 0;
 #pragma unroll
@@ -292,6 +387,12 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ qnoise
     }
 }
 
+// 0: 8-pass radix select (default); 1: bucket select (RQB200_SAMPLER_V2=1, experiment for the next round)
+static int sampler_algo() {
+    const char* e = getenv("RQB200_SAMPLER_V2");
+    return (e && e[0] == '1') ? 1 : 0;
+}
+
 // out_stride: distance (in int64 elements) between consecutive rows' outputs -- lets the AR loop write straight into
 // codes[b, h, w, d] (stride H*W*D).  force (nullable) uses the same addressing.
 int launch_sample(const float* logits, const float* q, int B, int V, float temperature, int top_k, float top_p,
@@ -308,7 +409,7 @@ int launch_sample(const float* logits, const float* q, int B, int V, float tempe
         attr = SMP_MAXV * 12;
     }
     sample_kernel<<<B, SMP_THREADS, smem, st>>>(logits, q, V, temperature, top_k, top_p, out_idx, force, out_stride, nullptr, 0, 0,
-                                                0);
+                                                0, sampler_algo());
     return check_launch("sample_logits");
 }
 
@@ -333,7 +434,7 @@ int launch_sample_dyn(const float* logits, const StepState* stt, int d, int B, i
     cfg.attrs = at;
     cfg.numAttrs = 1;
     RQB_CUDA(cudaLaunchKernelEx(&cfg, sample_kernel, logits, (const float*)nullptr, V, 1.0f, 0, 1.0f, (int64_t*)nullptr,
-                                (const int64_t*)nullptr, (int64_t)0, stt, d, HW, D));
+                                (const int64_t*)nullptr, (int64_t)0, stt, d, HW, D, sampler_algo()));
     g_launches++;
     return 0;
 }

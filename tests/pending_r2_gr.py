@@ -203,3 +203,35 @@ def test_vae_fast_tier_encode_within_1e3(golden, layouts, name):
         assert mism <= max(2, codes.numel() // 50)
     finally:
         del os.environ["RQB200_ENC_FAST"]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# sampler: bucket select for the top-k threshold (csrc/sampler.cu, RQB200_SAMPLER_V2=1) against the radix select, which is pinned
+# to the reference's golden vectors in tests/test_gpu_parity.py -- the emitted indices must be identical.
+@pytest.mark.parametrize("V", [512, 2048, 16384])
+@pytest.mark.parametrize("k", [1, 7, 250, 1024])
+@pytest.mark.parametrize("p", [None, 0.95])
+def test_sampler_v2_identical_to_v1(V, k, p):
+    from rqvae.models import _bind as nb
+    if k >= V:
+        pytest.skip("top-k disabled")
+    B = 64
+    lg = synth.randn_seeded((B, V), 21).to(DEV) * 3
+    lg[1] = torch.round(lg[1])                       # heavy ties
+    lg[2] = 0.5                                      # all equal (degenerate range -> radix path)
+    lg[3, ::3] = float("-inf")                       # non-finite entries -> radix path
+    lg[4] = lg[4] * 1e-3 + 100.0                     # narrow range far from zero
+    lg[5, : V // 2] = lg[5, 0]                       # half the row equal: overfull bucket
+    q = synth.exp_noise(5, 0, B, V).to(DEV)
+
+    def run(v2):
+        if v2:
+            os.environ["RQB200_SAMPLER_V2"] = "1"
+        try:
+            return nb.sample_logits(lg, 0.9, k, p, q=q), nb.sample_logits(lg, 1.0, k, p, q=None)
+        finally:
+            os.environ.pop("RQB200_SAMPLER_V2", None)
+
+    a1, g1 = run(False)
+    a2, g2 = run(True)
+    assert torch.equal(a1, a2) and torch.equal(g1, g2)

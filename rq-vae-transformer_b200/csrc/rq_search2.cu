@@ -84,7 +84,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R2_THREADS, 1)
 rq_quantize2_kernel(const __grid_constant__ CUtensorMap tmCB, const float* __restrict__ x, const float* __restrict__ cb, int64_t N,
                     int K, int D, int64_t* __restrict__ codes, float* __restrict__ quant_list, float* __restrict__ resid_out) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024 B alignment (swizzle atom) by an OFFSET into the shared array: keeps the pointers in the shared address space, so the
+    // hot loop compiles to LDS.128 and not to generic LD
+    uint8_t* ring = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     Rq2Smem& s = *reinterpret_cast<Rq2Smem*>(ring + R2_STAGES * R2_STAGE_BYTES);
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;

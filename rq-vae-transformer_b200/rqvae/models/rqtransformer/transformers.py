@@ -54,6 +54,14 @@ class _Stack(_Holder):
         self.blocks = nn.ModuleList([_Block(cfg.block) for _ in range(cfg.n_layer)])
 
 
+def fold_layernorm(W, bias, gamma, beta):
+    """Linear(LayerNorm(x)) = rstd * (W' x - mean * c) + b'  with  W' = W diag(gamma), b' = W beta + bias, c_n = sum_k W'[n, k].
+    c is summed over the bf16-ROUNDED W' (the operand the tensor cores see) so that the mean term cancels exactly.
+    Returns (W' fp32 -- the caller rounds it to bf16 --, b', c)."""
+    Wf = W * gamma[None, :]
+    return Wf, W @ beta + bias, Wf.to(torch.bfloat16).float().sum(1)
+
+
 class RQTransformer(Stage2Model):
     def __init__(self, config):
         super().__init__()
@@ -168,10 +176,8 @@ class RQTransformer(Stage2Model):
                   and os.environ.get("RQB200_GR", "0") == "1")
 
         def folded(W, bias, ln):
-            W, bias = W.detach().float(), bias.detach().float()
-            Wf = W * ln.weight.detach().float()[None, :]
-            c = Wf.to(torch.bfloat16).float().sum(1)
-            return wt(Wf), f32(W @ ln.bias.detach().float() + bias), f32(c)
+            Wf, d, c = fold_layernorm(W.detach().float(), bias.detach().float(), ln.weight.detach().float(), ln.bias.detach().float())
+            return wt(Wf), f32(d), f32(c)
 
         def blocks(stack):
             arr = (N.BlockWeights * len(stack.blocks))()

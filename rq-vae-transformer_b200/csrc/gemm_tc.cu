@@ -108,8 +108,9 @@ __device__ __forceinline__ float gr_warp_sum(float v) {
 
 __device__ __noinline__ void gr_reduce_tail(const GemmTcParams& p, int tile, int split, int ew, int lane) {
     const int S = p.splits;
-    // 1. publish this CTA's partial tile, wait for the S - 1 peers of the tile
-    __threadfence();
+    // 1. publish this CTA's partial tile, wait for the S - 1 peers of the tile.  One gpu-scope release by one thread AFTER the
+    //    CTA barrier covers every epilogue thread's stores (release is cumulative over what the barrier ordered before it) --
+    //    the pattern of a cooperative-groups grid sync; no per-thread fence.
     gr_bar_epilogue();
     if (ew == 0 && lane == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.gr_counter + tile), "r"(1u) : "memory");

@@ -310,6 +310,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const int b = c0 + i;
                 if (b >= p.B) break;
                 float v = __uint_as_float(r4[c][i]) + bias;
+                if constexpr (GR) {      // group-reduce instantiation: the partial tile goes to the tile-major L2 scratch
+                    __stcg(p.gr_scratch + (((int64_t)tile * p.splits + split) * p.B + b) * 128 + (q * 32 + lane), v);
+                    continue;
+                }
                 switch (p.mode) {
                     case GT_F32:
                         if (res) v += res[(int64_t)b * p.ld_res + n];
@@ -324,8 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     case GT_PARTIAL:
                         p.partial[((int64_t)split * p.B + b) * p.N_out + n] = v;
                         break;
-                    case GT_GR:
-                        if (GR) __stcg(p.gr_scratch + (((int64_t)tile * p.splits + split) * p.B + b) * 128 + (q * 32 + lane), v);
+                    default:
                         break;
                 }
             }

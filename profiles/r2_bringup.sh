@@ -20,7 +20,8 @@ step sampler_v2            300 python -m pytest tests/pending_r2_gr.py -m gpu -q
 step enc_fast              300 python -m pytest tests/pending_r2_gr.py -m gpu -q -k "fast_tier_encode"
 step gr_chain_tiny         300 python -m pytest tests/pending_r2_gr.py -m gpu -q -k "gr_chain and (tiny or consistency)"
 step gr_chain_big          600 python -m pytest tests/pending_r2_gr.py -m gpu -q -k "gr_chain and (ffhq355m or in1400m)"
-step exp_env               300 python profiles/exp_env.py "" "RQB200_GEMM_STAGES=4,RQB200_GEMM_L2PF=1" "RQB200_GR=1" "RQB200_GR=1,RQB200_LNFOLD=1" \
+step exp_env               300 python profiles/exp_env.py "" "RQB200_GEMM_STAGES=4,RQB200_GEMM_L2PF=1" "RQB200_GEMM_STAGES=4,RQB200_GEMM_RELINQ=1" \
+                               "RQB200_GEMM_STAGES=4,RQB200_GEMM_L2PF=1,RQB200_GEMM_RELINQ=1" "RQB200_GEMM_STAGES=3,RQB200_GEMM_L2PF=1,RQB200_GEMM_RELINQ=1" "RQB200_GR=1" "RQB200_GR=1,RQB200_LNFOLD=1" \
                                "RQB200_GR=1,RQB200_LNFOLD=1,RQB200_GEMM_STAGES=4,RQB200_GEMM_L2PF=1" "RQB200_SAMPLER_V2=1" \
                                "RQB200_GR=1,RQB200_LNFOLD=1,RQB200_SAMPLER_V2=1"
 step rq_v1                 120 python profiles/prof_rq.py 64 16384
@@ -28,6 +29,6 @@ RQB200_RQ_V2=1 step rq_v2_time 120 python profiles/prof_rq.py 64 16384
 step sampler_v1            120 python profiles/bench_sampler.py
 RQB200_SAMPLER_V2=1 step sampler_v2_time 120 python profiles/bench_sampler.py
 step gemm_iso              120 python profiles/bench_gemm.py
-RQB200_GEMM_STAGES=4 RQB200_GEMM_L2PF=1 step gemm_iso_s4 120 python profiles/bench_gemm.py
+RQB200_GEMM_STAGES=4 RQB200_GEMM_L2PF=1 RQB200_GEMM_RELINQ=1 step gemm_iso_s4 120 python profiles/bench_gemm.py
 step chain                 120 python profiles/bench_chain.py
 echo "----"; cat $OUT/summary.txt

@@ -220,7 +220,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, TMEM_COLS);
+        if (p.relinq) tc::tmem_relinquish();
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -414,6 +417,7 @@ static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, cons
 int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p_in, bool pdl, cudaStream_t st) {
     GemmTcParams p = p_in;
     if (const char* e = getenv("RQB200_GEMM_L2PF")) p.l2pf = atoi(e);
+    if (const char* e = getenv("RQB200_GEMM_RELINQ")) p.relinq = atoi(e);
     if (p.K % 64 != 0 || p.N_out % 128 != 0) return fail(RQB200_EINVAL, "gemm_tc: need K % 64 == 0 and N_out % 128 == 0");
     if (p.B < 1 || p.B > 256) return fail(RQB200_EINVAL, "gemm_tc: batch rows must be in [1,256]");
     if (p.splits < 1 || p.splits > p.K / 64) return fail(RQB200_EINVAL, "gemm_tc: bad split count");

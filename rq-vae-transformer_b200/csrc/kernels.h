@@ -79,6 +79,7 @@ struct GemmTcParams {
     float* partial;               // GT_PARTIAL: [splits][B][N_out] f32 (no bias)
     int w_tiled;                  // 1: W is stored tile-major [N_out/128][K/64][128][64] (each TMA box = 16 KB contiguous in HBM)
     int l2pf;                     // 1: before waiting for the upstream kernel, prefetch into L2 the weight boxes that do not fit the ring
+    int relinq;                   // 1: tcgen05.relinquish_alloc_permit right after the TMEM allocation (matters once two GEMM CTAs share an SM)
     // GT_GR ("group reduce"): split-K whose reduction happens INSIDE the kernel.  Every split CTA stores its fp32 partial tile to
     // gr_scratch (stays in L2), signals the tile's arrival counter, waits for its `splits` peers and then reduces its own slice of
     // the batch rows in a fixed split order (deterministic) and applies the epilogue -- no separate reduction launch.

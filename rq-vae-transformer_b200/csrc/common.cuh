@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/rqb200.h"
@@ -32,6 +33,20 @@ inline int check_launch(const char* what) {
     do {                                                                                   \
         cudaError_t _e = (expr);                                                           \
         if (_e != cudaSuccess) return rqb::fail(RQB200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember it per (call site, device), thread-safe.
+// usage: RQB_ENSURE_SMEM(bytes, kernel<template, args>);
+#define RQB_ENSURE_SMEM(bytes, ...)                                                                               \
+    do {                                                                                                          \
+        static std::atomic<uint64_t> _done{0};                                                                    \
+        int _dev = 0;                                                                                             \
+        RQB_CUDA(cudaGetDevice(&_dev));                                                                           \
+        const uint64_t _bit = 1ull << (_dev & 63);                                                                \
+        if (!(_done.load(std::memory_order_acquire) & _bit)) {                                                    \
+            RQB_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _done.fetch_or(_bit, std::memory_order_release);                                                      \
+        }                                                                                                         \
     } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -88,6 +103,30 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
     float r = (lane < nw) ? scratch[lane] : -INFINITY;
     r = warp_max(r);
     return r;
+}
+
+// 16-bit tensor-core operand storage of the fast tier.  `bf` selects the format at run time (uniform per launch): 0 = IEEE fp16
+// (the reference's autocast class, transformers.py:114,206), 1 = bf16.  Same bytes, same tcgen05 kind::f16 rate.
+typedef uint16_t h16;
+__device__ __forceinline__ uint32_t pack_h16x2(float a, float b, int bf) {
+    if (bf) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h16x2(uint32_t v, int bf) {
+    if (bf) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+    return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+__device__ __forceinline__ h16 pack_h16(float a, int bf) {
+    if (bf) {
+        __nv_bfloat16 h = __float2bfloat16(a);
+        return *reinterpret_cast<h16*>(&h);
+    }
+    __half h = __float2half_rn(a);
+    return *reinterpret_cast<h16*>(&h);
 }
 
 template <typename T>

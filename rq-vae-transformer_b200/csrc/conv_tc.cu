@@ -189,11 +189,7 @@ static int launch_conv_tc_t(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
                             const ConvTcParams& p, int n_sm, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (PASSES == 3 ? 2 : 1) * (CT_A_BYTES + BN * 128) + 1024 + 256;
     static_assert(smem <= 227 * 1024, "conv_tc: shared memory budget");
-    static bool attr = false;
-    if (!attr) {
-        RQB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    RQB_ENSURE_SMEM(smem, conv_tc_kernel<BN, STAGES, PASSES>);
     const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles_n;
     const int grid = total < n_sm ? total : n_sm;
     conv_tc_kernel<BN, STAGES, PASSES><<<grid, CT_THREADS, smem, st>>>(tmA, tmB, tmAlo, tmBlo, p);

@@ -387,11 +387,7 @@ template <int BN, int STAGES, bool CL, bool GR = false>
 static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (GT_A_BYTES + BN * 128) + 1024 + 256;
     static_assert(!CL || (size_t)STAGES * (GT_A_BYTES + BN * 128) >= (size_t)128 * (BN + 1) * 4, "staging area must fit in the ring");
-    static bool attr = false;
-    if (!attr) {
-        RQB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CL, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    RQB_ENSURE_SMEM(smem, gemm_tc_kernel<BN, STAGES, CL, GR>);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ceil_div(p.N_out, 128) * p.splits));
     cfg.blockDim = dim3(GT_THREADS);

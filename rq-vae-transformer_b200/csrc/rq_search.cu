@@ -254,11 +254,7 @@ int launch_rq_quantize(const float* x, const float* cb, int64_t N, int K, int C,
     // experiment for the next round (csrc/rq_search2.cu): same arithmetic, 8x8 register tile, 2-CTA clusters splitting the codebook
     if (const char* e = getenv("RQB200_RQ_V2"))
         if (e[0] == '1' && rq_quantize2_supported(N, K, C)) return launch_rq_quantize2(x, cb, N, K, C, D, codes, quant_list, resid_out, st);
-    static bool attr_set = false;
-    if (!attr_set) {
-        RQB_CUDA(cudaFuncSetAttribute(rq_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RqSmem)));
-        attr_set = true;
-    }
+    RQB_ENSURE_SMEM(sizeof(RqSmem), rq_quantize_kernel);
     unsigned grid = (unsigned)ceil_div(N, RQ_TN);
     rq_quantize_kernel<<<grid, RQ_THREADS, sizeof(RqSmem), st>>>(x, cb, N, K, D, codes, quant_list, resid_out);
     return check_launch("rq_quantize");

@@ -292,11 +292,7 @@ int launch_rq_quantize2(const float* x, const float* cb, int64_t N, int K, int C
     CUtensorMap tm;
     RQB_TRY(make_tmap_2d(&tm, cb, 2, (uint64_t)R2_C, (uint64_t)K, (uint64_t)R2_C * 4, R2_CC, R2_KB));
     const size_t smem = (size_t)R2_STAGES * R2_STAGE_BYTES + sizeof(Rq2Smem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RQB_CUDA(cudaFuncSetAttribute(rq_quantize2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    RQB_ENSURE_SMEM(smem, rq_quantize2_kernel);
     const unsigned grid = 2u * (unsigned)ceil_div(N, R2_TN);
     rq_quantize2_kernel<<<grid, R2_THREADS, smem, st>>>(tm, x, cb, N, K, D, codes, quant_list, resid_out);
     return check_launch("rq_quantize2");

@@ -403,11 +403,7 @@ int launch_sample(const float* logits, const float* q, int B, int V, float tempe
     int vpad = 1;
     while (vpad < V) vpad <<= 1;
     size_t smem = (size_t)V * sizeof(float) + (top_p < 1.0f ? (size_t)vpad * sizeof(SortItem) : 0);
-    static size_t attr = 0;
-    if (smem > attr) {
-        RQB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMP_MAXV * 12)));
-        attr = SMP_MAXV * 12;
-    }
+    RQB_ENSURE_SMEM(SMP_MAXV * 12, sample_kernel);
     sample_kernel<<<B, SMP_THREADS, smem, st>>>(logits, q, V, temperature, top_k, top_p, out_idx, force, out_stride, nullptr, 0, 0,
                                                 0, sampler_algo());
     return check_launch("sample_logits");
@@ -418,11 +414,7 @@ int launch_sample_dyn(const float* logits, const StepState* stt, int d, int B, i
     int vpad = 1;
     while (vpad < V) vpad <<= 1;
     size_t smem = (size_t)V * sizeof(float) + (size_t)vpad * sizeof(SortItem);   // top_p is only known on the device
-    static bool attr = false;
-    if (!attr) {
-        RQB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMP_MAXV * 12)));
-        attr = true;
-    }
+    RQB_ENSURE_SMEM(SMP_MAXV * 12, sample_kernel);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B);
     cfg.blockDim = dim3(SMP_THREADS);

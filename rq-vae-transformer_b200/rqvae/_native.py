@@ -137,4 +137,10 @@ def default_precision():
     return os.environ.get("RQB200_PRECISION", "auto")
 
 
+def param_fingerprint(module):
+    """identity + in-place-write counter of every parameter / buffer.  The native engines cache packed weight copies; they are
+    rebuilt when this changes (nested load_state_dict through a wrapper, EMA updates, optimizer steps, .data swaps)."""
+    return hash(tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers())))
+
+
 launch_count = {"total": 0}      # kernels launched by our library through this binding (bench.py's gpu_launches)

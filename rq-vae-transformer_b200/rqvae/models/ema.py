@@ -15,7 +15,8 @@ class ExponentialMovingAverage(nn.Module):
 
     @torch.no_grad()
     def update(self, module, step=None):
-        mu = 0.0 if step is None or step < 0 else min(self.mu, (1.0 + step) / (10.0 + step))
+        # rqvae/models/ema.py:30-43: step None -> self.mu; step < 0 -> hard copy; else the warm-up schedule
+        mu = self.mu if step is None else (0.0 if step < 0 else min(self.mu, (1.0 + step) / (10.0 + step)))
         src = dict(module.state_dict())
         for name, dst in self.module.state_dict().items():
             s = src[name].to(dst.device)

@@ -99,6 +99,7 @@ class RQTransformer(Stage2Model):
                                                               ("linear", nn.Linear(E, config.vocab_size_cond))]))
         self.precision = None
         self._eng = {}
+        self._eng_fp = None
         self._cache = None
         self.last_launches = 0
 
@@ -140,6 +141,10 @@ class RQTransformer(Stage2Model):
 
     def _engine(self, codebook, mode, slot=0):
         dev = self.pos_emb_hw.device
+        fp = (N.param_fingerprint(self), codebook._version)
+        if fp != self._eng_fp:               # weights changed behind the module's own hooks (wrapper load, in-place write)
+            self._invalidate_native()
+            self._eng_fp = fp
         key = (str(dev), mode, codebook.data_ptr(), slot)
         if key not in self._eng and slot > 0:
             # engines of one model share the packed weights of slot 0; each slot owns its workspace, KV cache and graphs

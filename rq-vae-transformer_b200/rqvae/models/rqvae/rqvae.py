@@ -39,6 +39,7 @@ class RQVAE(Stage1Model):
         self.precision = None            # None -> _native.default_precision() ('auto' == exact until told otherwise)
         self.split_fp16 = True           # fast tier: 3-product split-fp16 convs (keeps 60 chained convs within 1e-3)
         self._eng = {}                   # (device, mode) -> dict(handle, tensors, ws)
+        self._eng_fp = None              # parameter fingerprint the cached engines were built from
         self.last_launches = 0
 
     # ------------------------------------------------------------------ native engine plumbing
@@ -67,6 +68,10 @@ class RQVAE(Stage1Model):
 
     def _engine(self, device):
         mode = self._mode()
+        fp = N.param_fingerprint(self)
+        if fp != self._eng_fp:               # weights changed behind the module's own hooks (wrapper load, in-place write)
+            self._invalidate_native()
+            self._eng_fp = fp
         key = (str(device), mode, self.split_fp16)
         if key in self._eng:
             return self._eng[key]

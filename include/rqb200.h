@@ -35,10 +35,18 @@ extern "C" {
 
 /* arithmetic modes (DESIGN.md "two modes") */
 #define RQB200_MODE_EXACT 0  /* fp32 weights + fp32 FFMA: the bit-exact-indices gate                    */
-#define RQB200_MODE_FAST 1   /* bf16 (AR) / fp16 (conv) operands on tcgen05, fp32 accumulate: throughput */
-/* OR-ed into rqb200_ar_config.mode (fast tier): every weight matrix [N,K] is stored tile-major, [N/128][K/64][128][64], so that
- * each 128x64 TMA box is 16 KB of CONTIGUOUS HBM (a row-major matrix gives 128 scattered 128 B segments per box) */
-#define RQB200_WEIGHTS_TILED 0x100
+#define RQB200_MODE_FAST 1   /* fp16 (default) or bf16 operands on tcgen05, fp32 accumulate: throughput  */
+
+/* rqb200_ar_config.flags (fast tier; scheduling only -- none of them changes a result bit, except SEQUENTIAL_PREFILL's
+ * summation order) */
+#define RQB200_AR_NO_GRAPH 1            /* launch kernel by kernel instead of replaying CUDA graphs                        */
+#define RQB200_AR_NO_PDL 2              /* plain stream order instead of programmatic dependent launch                     */
+#define RQB200_AR_TRACE 4               /* record 4 globaltimer stamps per launch (rqb200_ar_trace)                        */
+#define RQB200_AR_L2_PREFETCH 8         /* GEMMs prefetch into L2 the weight boxes that do not fit their shared-memory ring */
+#define RQB200_AR_SHALLOW_RING 16       /* half-depth GEMM rings: two GEMM CTAs of consecutive launches share an SM        */
+#define RQB200_AR_SEQUENTIAL_PREFILL 32 /* prefill the prefix token by token with the single-step graph (the prefill oracle) */
+#define RQB200_AR_NO_NEXT_PREFETCH 64   /* fc1 does not pull fc2's weights into L2                                          */
+#define RQB200_AR_LN_CLUSTER 128        /* reduction + LayerNorm rows split over 2-CTA clusters (DSMEM statistics exchange)  */
 
 const char* rqb200_last_error(void);
 int rqb200_version(void);
@@ -74,10 +82,6 @@ typedef struct rqb200_block_weights {
     const void *wqkv, *wproj, *w1, *w2;            /* [3E,E] (rows: query|key|value), [E,E], [4E,E], [E,4E]; weight dtype */
     const float *bqkv, *bproj, *b1, *b2;           /* f32 biases */
     const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;    /* f32 */
-    /* Optional (fast tier only, NULL otherwise): LayerNorm folded into the following Linear.  When cqkv / c1 are non-NULL,
-     * wqkv / w1 hold W*diag(ln_w), bqkv / b1 hold W*ln_b + b, and cqkv [3E] / c1 [4E] hold c_n = sum_k bf16(W*diag(ln_w))[n,k], so
-     * that Linear(LayerNorm(x))[n] = rstd*(W'x - mean*c_n) + b'_n with the row statistics applied in the GEMM epilogue. */
-    const float *cqkv, *c1;
 } rqb200_block_weights;
 
 typedef struct rqb200_ar_config {
@@ -86,7 +90,9 @@ typedef struct rqb200_ar_config {
     int32_t vocab_cond, cond_len;                       /* cond_emb rows, block_size_cond (>=1)                */
     int32_t code_dim, codebook_size;                    /* C (=256) and K of the RQ-VAE codebook               */
     int32_t mode;                                       /* RQB200_MODE_*                                       */
-    int32_t weight_dtype;                               /* RQB200_F32 (exact) or RQB200_BF16 (fast)            */
+    int32_t weight_dtype;                               /* RQB200_F32 (exact); RQB200_F16 or RQB200_BF16 (fast) */
+    int32_t flags;                                      /* fast tier: RQB200_AR_* flags                         */
+    int32_t split_qkv, split_proj, split_fc1, split_fc2; /* fast tier: split-K factors, 0 = fill the SMs        */
 } rqb200_ar_config;
 
 typedef struct rqb200_ar_weights {
@@ -120,6 +126,18 @@ int rqb200_ar_sample(rqb200_ar* h, const int64_t* partial, const int64_t* cond, 
                      float temperature, const int32_t* top_k_host, const float* top_p_host, const float* noise,
                      int64_t noise_stride, float* logits_out, const int64_t* force_codes, int64_t* out_codes,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* The same loop over the positions [idx_begin, idx_end) of the raster only.  resume == 0: starts like rqb200_ar_sample with
+ * start_loc = idx_begin (prefix prefill from `partial`); resume != 0: continues on the KV / context state the previous call left
+ * in the SAME workspace (no prefill; `partial` is ignored, out_codes must be the buffer of the previous call).  noise /
+ * logits_out are indexed from the first token of THIS span.  Lets a caller draw the per-token noise in bounded chunks. */
+int rqb200_ar_sample_span(rqb200_ar* h, const int64_t* partial, const int64_t* cond, int B, int idx_begin, int idx_end, int resume,
+                          float temperature, const int32_t* top_k_host, const float* top_p_host, const float* noise,
+                          int64_t noise_stride, float* logits_out, const int64_t* force_codes, int64_t* out_codes,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* fast tier with RQB200_AR_TRACE: copies 4 globaltimer stamps (ns: entry, dependency resolved, accumulator ready / mid, done) per
+ * launch slot of the last graph replays to out_host[cap_launches][4] and the slot names ('\n'-separated) to names; returns the
+ * number of slots (0 when tracing is off).  Synchronises the device. */
+int rqb200_ar_trace(rqb200_ar* h, long long* out_host, int cap_launches, char* names, int names_cap);
 /* number of kernels the last rqb200_ar_sample call launched (bench.py's gpu_launches) */
 int64_t rqb200_ar_last_launches(const rqb200_ar* h);
 
@@ -157,22 +175,21 @@ int64_t rqb200_vae_last_launches(const rqb200_vae* h);
 /* ------------------------------------------------------------------------------------------------ diagnostics
  * Single-kernel entry points used by tests/ and bench.py's roofline leg; not part of the reference-facing surface.
  * rqb200_dbg_gemm_tc: one launch of the tcgen05 weight-streaming GEMM (csrc/gemm_tc.cu):
- *   out[b, n] = act(sum_k W[n,k] X[b,k] + bias[n]) (+ residual[b,n]);  W [N_out,K] bf16, X [B,K] bf16;
- *   splits > 1: partial [splits,B,N_out] f32 receives the per-split sums instead (no act / residual); partial == NULL with
- *   splits > 1 reduces inside the kernel (thread-block cluster, <= 8 splits).  splits < 0: W is tile-major (RQB200_WEIGHTS_TILED)
- *   and |splits| is the split count. */
-int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out,
-                       int out_is_bf16, int gelu, float* partial, int N_out, int K, int B, int splits, void* stream);
+ *   out[b, n] = act(sum_k W[n,k] X[b,k] + bias[n]) (+ residual[b,n]);  W [N_out,K], X [B,K] both 16-bit: fmt 0 = fp16, 1 = bf16;
+ *   partial != NULL: partial [splits,B,N_out] f32 receives the per-split sums instead (no bias / act / residual; B <= 256).
+ *   B > 256 (splits == 1) runs as row chunks of 256 (the batched-prefill / teacher-forced-forward shape). */
+int rqb200_dbg_gemm_tc(const void* W16, const void* X16, const float* bias, const float* residual, void* out,
+                       int out_is_16, int gelu, float* partial, int N_out, int K, int B, int splits, int fmt, void* stream);
 
-/* rqb200_dbg_gemm_gr: one launch of the same GEMM in its "group reduce" form (split-K reduced inside the kernel through an fp32
- * scratch [N_out/128][splits][B][128] and one arrival counter per 128-feature tile; needs (N_out/128)*splits <= SM count).
- * kind 0: out f32 [B,N_out] = sum + bias + residual, optional bf16 copy (out_bf16) and per-tile LayerNorm statistics
- * stats_out [B][N_out/128][2] = (sum, M2 about the tile mean); kind 1: out bf16 = gelu(sum + bias).  stats_in / fold_c (both or
- * neither): W holds W*diag(gamma), bias holds W*beta + b, fold_c[n] = sum_k W'[n,k] and stats_in [B][K/128][2] are the tile
- * statistics of the raw input rows: out = act(rstd_b*(sum - mean_b*fold_c[n]) + bias[n]). */
-int rqb200_dbg_gemm_gr(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out, int kind,
-                       float* scratch, unsigned* counters, void* out_bf16, float* stats_out, const float* stats_in,
-                       const float* fold_c, int N_out, int K, int B, int splits, void* stream);
+/* rqb200_dbg_rq_quantize: rqb200_rq_quantize with the kernel form forced: 1 = csrc/rq_search.cu (2x4 register tile), 2 =
+ * csrc/rq_search2.cu (8x8 register tile, 2-CTA clusters splitting the codebook; fails with RQB200_EINVAL for shapes it does not
+ * take), 0 = what rqb200_rq_quantize picks.  Both forms are bit-identical (tests/test_gpu_parity.py). */
+int rqb200_dbg_rq_quantize(int form, const float* x, const float* codebook, int64_t N, int K, int C, int D, int64_t* codes,
+                           float* quant_list, float* residual_out, void* stream);
+/* rqb200_dbg_sample_logits: rqb200_sample_logits with the top-k threshold search forced: 0 = 8-pass radix select, 1 = bucket
+ * select (the default).  Identical indices. */
+int rqb200_dbg_sample_logits(int algo, const float* logits, const float* q, int B, int V, float temperature, int top_k,
+                             float top_p, int64_t* out_idx, void* stream);
 
 /* rqb200_dbg_conv_tc: one launch of the tcgen05 implicit-GEMM conv (csrc/conv_tc.cu): X NHWC fp16 [B,H,W,Cin], W OHWI fp16
  * [Cout,ks,ks,Cin], stride 1 "same" padding, out f32 NHWC (+bias, +residual) or NCHW when out_nchw.  X16lo / W16lo

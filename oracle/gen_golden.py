@@ -138,8 +138,18 @@ def gen_sampler(ns, out):
     out["sampler"] = cases
 
 
+def gen_ar2(ns, out):
+    """second batch of AR fixtures (tests/golden/ar2.pt): the text-conditioned BASELINE shapes (configs 4 / 5) -- 32-token prefix
+    prefill, the synthetic 16x16x4 grid, the 3.9B widths.  Same protocol as gen_ar."""
+    plan = [
+        ("cc3m654m", 2, [dict(top_k=1), dict(top_k=1024, top_p=0.95)], [0, 1, 4, 255]),
+        ("cc3m654m_16", 2, [dict(top_k=1024, top_p=0.95)], [0, 5, 1023]),
+        ("t2i3900m", 2, [dict(top_k=1024, top_p=0.95)], [0, 1, 7, 255]),
+    ]
+    out["ar"] = _gen_ar_plan(ns, plan, keep_logits_of=lambda si: True)
+
+
 def gen_ar(ns, out):
-    res = {}
     plan = [
         # name, B, vae codebook K(=V), settings list, logits steps to keep
         ("tiny", 3, [dict(top_k=1), dict(top_k=100, top_p=0.9), dict()], list(range(0, 64, 5))),
@@ -147,6 +157,11 @@ def gen_ar(ns, out):
         ("ffhq355m", 2, [dict(top_k=1), dict(top_k=1024)], [0, 1, 2, 3, 4, 5, 100, 255]),
         ("in1400m", 2, [dict(top_k=1), dict(top_k=1024)], [0, 3, 4, 255]),
     ]
+    out["ar"] = _gen_ar_plan(ns, plan, keep_logits_of=lambda si: si == 0)
+
+
+def _gen_ar_plan(ns, plan, keep_logits_of):
+    res = {}
     for name, B, settings, keep in plan:
         t0 = time.time()
         model, sd = build_ar(ns, name, seed=11)
@@ -177,7 +192,7 @@ def gen_ar(ns, out):
                 codes = model.sample(torch.zeros(B, *bs, dtype=torch.long), model_aux=Aux(), cond=cond, **st)
             model.cached_forward = orig_cf
             runs.append(dict(setting=st, noise_seed=500 + si, codes=codes.to(torch.int32),
-                             logits={k: v for k, v in kept.items()} if si == 0 else None))
+                             logits={k: v for k, v in kept.items()} if keep_logits_of(si) else None))
         # start_loc resume (image completion): keep the first rows of run 0, resample from (h0, w0)
         h0, w0 = bs[0] // 2, 1
         part = runs[0]["codes"].long().clone()
@@ -188,7 +203,7 @@ def gen_ar(ns, out):
                                      top_k=settings[-1].get("top_k")))
         print("  ar %-10s %.1fs" % (name, time.time() - t0), flush=True)
         del model
-    out["ar"] = res
+    return res
 
 
 def gen_vae(ns, out):
@@ -220,7 +235,7 @@ def gen_vae(ns, out):
 def gen_layouts(ns):
     lay = {}
     for name in AR_ZOO:
-        if name in ("in1400m", "cc3m654m", "ffhq355m"):
+        if AR_ZOO[name][0] >= 1024:
             with torch.device("meta"):
                 m = ns.RQTransformer(ar_cfg(name))
         else:
@@ -238,8 +253,8 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     ns = R.load_reference()
     check_multinomial_identity()
-    which = sys.argv[1:] or ["rq", "sampler", "ar", "vae", "layouts"]
-    for part, fn in (("rq", gen_rq), ("sampler", gen_sampler), ("ar", gen_ar), ("vae", gen_vae)):
+    which = sys.argv[1:] or ["rq", "sampler", "ar", "vae", "ar2", "layouts"]
+    for part, fn in (("rq", gen_rq), ("sampler", gen_sampler), ("ar", gen_ar), ("vae", gen_vae), ("ar2", gen_ar2)):
         if part in which:
             out = {}
             t0 = time.time()

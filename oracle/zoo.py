@@ -8,6 +8,10 @@ AR_ZOO = {
     "ffhq355m": (1024, 16, 24, 4, 2048, (8, 8, 4), 1, 1),        # configs/ffhq/stage2/ffhq256-rqtransformer-8x8x4-350M.yaml:7-30
     "in1400m": (1536, 24, 42, 6, 16384, (8, 8, 4), 1000, 1),     # configs/imagenet256/stage2/in256-rqtransformer-8x8x4-1400M.yaml:7-30
     "cc3m654m": (1280, 20, 26, 4, 16384, (8, 8, 4), 16384, 32),  # configs/cc3m/cc3m-rqtransformer-8x8x4-650M.yaml:11-34
+    # BASELINE configs 4 / 5 shapes the reference does not ship as yaml (SURVEY finding 8): the 654M widths on a synthetic 16x16x4
+    # grid (measure_throughput f=16), and the "3.9B" text-to-image arch = the 3800M widths (README.md:47,72) + a 32-token prefix
+    "cc3m654m_16": (1280, 20, 26, 4, 16384, (16, 16, 4), 16384, 32),
+    "t2i3900m": (2560, 40, 42, 6, 16384, (8, 8, 4), 16384, 32),
 }
 VAE_ZOO = {
     "tiny": dict(K=512, code_shape=(4, 4, 4), ch=32, ch_mult=(1, 2, 4), attn_resolutions=(4,), resolution=16),

@@ -28,9 +28,9 @@ for name, n_out, k in shapes:
 
         def run(i):
             if splits == 1:
-                L.rqb200_dbg_gemm_tc(N.ptr(Ws[i % nw]), N.ptr(X), None, None, N.ptr(out), 0, 0, None, n_out, k, B, 1, st)
+                L.rqb200_dbg_gemm_tc(N.ptr(Ws[i % nw]), N.ptr(X), None, None, N.ptr(out), 0, 0, None, n_out, k, B, 1, 1, st)
             else:
-                L.rqb200_dbg_gemm_tc(N.ptr(Ws[i % nw]), N.ptr(X), None, None, None, 0, 0, N.ptr(part), n_out, k, B, splits, st)
+                L.rqb200_dbg_gemm_tc(N.ptr(Ws[i % nw]), N.ptr(X), None, None, None, 0, 0, N.ptr(part), n_out, k, B, splits, 1, st)
         for i in range(nw):
             run(i)
         torch.cuda.synchronize()

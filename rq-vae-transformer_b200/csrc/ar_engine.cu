@@ -7,6 +7,7 @@
 //   * only the NEW position's code embeddings are computed each step (reference re-embeds the whole prefix twice per
 //     token, transformers.py:217-220,249-255 -- row-wise identical values);
 //   * the sampled code is written on the device and consumed by the next step's kernels; nothing returns to the host.
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -68,7 +69,8 @@ static int run_stack(const rqb200_ar* h, const std::vector<rqb200_block_weights>
     return 0;
 }
 
-static int ar_sample_impl(rqb200_ar* h, const int64_t* partial, const int64_t* cond, int B, int start_h, int start_w,
+// positions [idx0, idx_end) of the raster; resume != 0: no prefill, continue on the caches / context left in this workspace
+static int ar_sample_impl(rqb200_ar* h, const int64_t* partial, const int64_t* cond, int B, int idx0, int idx_end, int resume,
                           float temperature, const int32_t* top_k, const float* top_p, const float* noise,
                           int64_t noise_stride, float* logits_out, const int64_t* force, int64_t* out, void* wsp,
                           size_t ws_bytes, cudaStream_t st) {
@@ -77,29 +79,30 @@ static int ar_sample_impl(rqb200_ar* h, const int64_t* partial, const int64_t* c
     const int E = c.embed_dim, D = c.D, HW = c.H * c.W, C = c.code_dim, V = c.vocab, K = c.codebook_size;
     const int wd = c.weight_dtype, cl = c.cond_len, Tb = cl + HW;
     if (B <= 0) return fail(RQB200_EINVAL, "ar_sample: B must be > 0");
-    if (start_h < 0 || start_w < 0 || start_w >= c.W || start_h > c.H) return fail(RQB200_EINVAL, "ar_sample: bad start_loc");
+    if (idx0 < 0 || idx_end > HW || idx0 > idx_end) return fail(RQB200_EINVAL, "ar_sample: bad position span");
     ArWs ws;
     size_t need = ar_layout(c, B, wsp, ws_bytes, &ws);
     if (need > ws_bytes) return fail(RQB200_EWORKSPACE, "ar_sample: workspace too small");
     const int64_t code_bytes = (int64_t)B * HW * D * sizeof(int64_t);
-    if (out != partial) RQB_CUDA(cudaMemcpyAsync(out, partial, code_bytes, cudaMemcpyDeviceToDevice, st));   // xs = partial_sample.clone()
-    const int idx0 = start_h * c.W + start_w;
-    if (idx0 >= HW) return 0;
+    if (!resume && out != partial) RQB_CUDA(cudaMemcpyAsync(out, partial, code_bytes, cudaMemcpyDeviceToDevice, st));   // xs = partial_sample.clone()
+    if (idx0 >= idx_end) return 0;
 
-    // ---- prefill: tokens [cond (cl) | xs_emb[0 .. idx0-1]]  (transformers.py:224-239)
-    const int Tn0 = cl + idx0;
-    RQB_TRY(launch_cond_token(cond, w.cond_emb, w.pos_emb_cond, B, cl, c.vocab_cond, E, Tn0, ws.X, st));
-    if (idx0 > 0) {
-        RQB_TRY(launch_code_emb(out, w.codebook, B, HW, D, K, C, 0, idx0, ws.EMB, st));
-        RQB_TRY(launch_linear(ws.EMB, C, w.w_in, wd, w.b_in, nullptr, ws.LIN, E, B * idx0 * D, E, C, 0, st));
-        RQB_TRY(launch_body_token(ws.LIN, w.pos_emb_hw, B, D, E, 0, idx0, cl, Tn0, ws.X, st));
+    if (!resume) {
+        // ---- prefill: tokens [cond (cl) | xs_emb[0 .. idx0-1]]  (transformers.py:224-239)
+        const int Tn0 = cl + idx0;
+        RQB_TRY(launch_cond_token(cond, w.cond_emb, w.pos_emb_cond, B, cl, c.vocab_cond, E, Tn0, ws.X, st));
+        if (idx0 > 0) {
+            RQB_TRY(launch_code_emb(out, w.codebook, B, HW, D, K, C, 0, idx0, ws.EMB, st));
+            RQB_TRY(launch_linear(ws.EMB, C, w.w_in, wd, w.b_in, nullptr, ws.LIN, E, B * idx0 * D, E, C, 0, st));
+            RQB_TRY(launch_body_token(ws.LIN, w.pos_emb_hw, B, D, E, 0, idx0, cl, Tn0, ws.X, st));
+        }
+        RQB_TRY(run_stack(h, h->body, ws, B, Tn0, 0, Tb, ws.kc_body, ws.vc_body, st));
+        RQB_TRY(launch_row_add(ws.X, (int64_t)Tn0 * E, (int64_t)(Tn0 - 1) * E, nullptr, B, E, ws.CTX, st));   // latents[:, -1]
     }
-    RQB_TRY(run_stack(h, h->body, ws, B, Tn0, 0, Tb, ws.kc_body, ws.vc_body, st));
-    RQB_TRY(launch_row_add(ws.X, (int64_t)Tn0 * E, (int64_t)(Tn0 - 1) * E, nullptr, B, E, ws.CTX, st));   // latents[:, -1]
 
     int64_t step = 0;
-    for (int idx = idx0; idx < HW; idx++) {
-        if (idx > idx0) {   // decode step on the token of position idx-1 (transformers.py:240-242)
+    for (int idx = idx0; idx < idx_end; idx++) {
+        if (idx > idx0 || resume) {   // decode step on the token of position idx-1 (transformers.py:240-242)
             RQB_TRY(launch_code_emb(out, w.codebook, B, HW, D, K, C, idx - 1, 1, ws.EMB, st));
             RQB_TRY(launch_linear(ws.EMB, C, w.w_in, wd, w.b_in, nullptr, ws.LIN, E, B * D, E, C, 0, st));
             RQB_TRY(launch_body_token(ws.LIN, w.pos_emb_hw, B, D, E, idx - 1, 1, 0, 1, ws.X, st));
@@ -139,7 +142,10 @@ rqb200_ar* rqb200_ar_create(const rqb200_ar_config* cfg, const rqb200_ar_weights
         rqb::set_error("ar_create: unsupported shape");
         return nullptr;
     }
-    if (cfg->weight_dtype != RQB200_F32 && cfg->weight_dtype != RQB200_BF16) { rqb::set_error("ar_create: weight dtype"); return nullptr; }
+    if (cfg->weight_dtype != RQB200_F32 && cfg->weight_dtype != RQB200_BF16 && cfg->weight_dtype != RQB200_F16) {
+        rqb::set_error("ar_create: weight dtype");
+        return nullptr;
+    }
     rqb200_ar* h = new rqb200_ar();
     h->cfg = *cfg;
     h->w = *w;
@@ -147,8 +153,8 @@ rqb200_ar* rqb200_ar_create(const rqb200_ar_config* cfg, const rqb200_ar_weights
     h->head.assign(w->head, w->head + cfg->n_head_layers);
     h->w.body = h->body.data();
     h->w.head = h->head.data();
-    if ((cfg->mode & 0xff) == RQB200_MODE_FAST) {
-        if (cfg->weight_dtype != RQB200_BF16) { rqb::set_error("ar_create: fast tier needs bf16 weights"); delete h; return nullptr; }
+    if (cfg->mode == RQB200_MODE_FAST) {
+        if (cfg->weight_dtype == RQB200_F32) { rqb::set_error("ar_create: fast tier needs fp16 or bf16 weights"); delete h; return nullptr; }
         h->fast = rqb::ar_fast_create(h->cfg, h->w, h->body.data(), h->head.data());
         if (!h->fast) { delete h; return nullptr; }
     }
@@ -163,26 +169,39 @@ size_t rqb200_ar_workspace_bytes(const rqb200_ar* h, int B) {
     if (h->fast) return rqb::ar_fast_workspace_bytes(h->fast, B);
     return rqb::ar_layout(h->cfg, B, nullptr, 0, nullptr);
 }
+int rqb200_ar_sample_span(rqb200_ar* h, const int64_t* partial, const int64_t* cond, int B, int idx_begin, int idx_end, int resume,
+                          float temperature, const int32_t* top_k_host, const float* top_p_host, const float* noise,
+                          int64_t noise_stride, float* logits_out, const int64_t* force_codes, int64_t* out_codes,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || (!partial && !resume) || !out_codes || !top_k_host || !top_p_host || !workspace)
+        return rqb::fail(RQB200_EINVAL, "ar_sample: null argument");
+    if (rqb200_device_count() <= 0) return rqb::fail(RQB200_ENODEV, "ar_sample: no CUDA device");
+    if (h->cfg.weight_dtype != RQB200_F32 && !h->fast) return rqb::fail(RQB200_EINVAL, "ar_sample: 16-bit weights need the fast tier");
+    rqb::g_launches = 0;
+    int rc;
+    if (h->fast)
+        rc = rqb::ar_fast_sample(h->fast, partial, cond, B, idx_begin, idx_end, resume, temperature, top_k_host, top_p_host, noise,
+                                 noise_stride, logits_out, force_codes, out_codes, workspace, workspace_bytes, (cudaStream_t)stream);
+    else
+        rc = rqb::ar_sample_impl(h, partial, cond, B, idx_begin, idx_end, resume, temperature, top_k_host, top_p_host, noise,
+                                 noise_stride, logits_out, force_codes, out_codes, workspace, workspace_bytes, (cudaStream_t)stream);
+    h->last_launches = rqb::g_launches;
+    return rc;
+}
 int rqb200_ar_sample(rqb200_ar* h, const int64_t* partial, const int64_t* cond, int B, int start_h, int start_w,
                      float temperature, const int32_t* top_k_host, const float* top_p_host, const float* noise,
                      int64_t noise_stride, float* logits_out, const int64_t* force_codes, int64_t* out_codes,
                      void* workspace, size_t workspace_bytes, void* stream) {
-    if (!h || !partial || !out_codes || !top_k_host || !top_p_host || !workspace)
-        return rqb::fail(RQB200_EINVAL, "ar_sample: null argument");
-    if (rqb200_device_count() <= 0) return rqb::fail(RQB200_ENODEV, "ar_sample: no CUDA device");
-    rqb::g_launches = 0;
-    if (h->fast) {
-        int rc = rqb::ar_fast_sample(h->fast, partial, cond, B, start_h, start_w, temperature, top_k_host, top_p_host, noise,
-                                     noise_stride, logits_out, force_codes, out_codes, workspace, workspace_bytes,
-                                     (cudaStream_t)stream);
-        h->last_launches = rqb::g_launches;
-        return rc;
-    }
-    int rc = rqb::ar_sample_impl(h, partial, cond, B, start_h, start_w, temperature, top_k_host, top_p_host, noise,
-                                 noise_stride, logits_out, force_codes, out_codes, workspace, workspace_bytes,
-                                 (cudaStream_t)stream);
-    h->last_launches = rqb::g_launches;
-    return rc;
+    if (!h) return rqb::fail(RQB200_EINVAL, "ar_sample: null argument");
+    if (start_h < 0 || start_w < 0 || start_w >= h->cfg.W || start_h > h->cfg.H) return rqb::fail(RQB200_EINVAL, "ar_sample: bad start_loc");
+    const int HW = h->cfg.H * h->cfg.W;
+    return rqb200_ar_sample_span(h, partial, cond, B, std::min(start_h * h->cfg.W + start_w, HW), HW, 0, temperature, top_k_host,
+                                 top_p_host, noise, noise_stride, logits_out, force_codes, out_codes, workspace, workspace_bytes, stream);
+}
+int rqb200_ar_trace(rqb200_ar* h, long long* out_host, int cap_launches, char* names, int names_cap) {
+    if (!h || !h->fast || !out_host) return 0;
+    cudaDeviceSynchronize();
+    return rqb::ar_fast_trace(h->fast, out_host, cap_launches, names, names_cap);
 }
 int64_t rqb200_ar_last_launches(const rqb200_ar* h) { return h ? h->last_launches : 0; }
 }

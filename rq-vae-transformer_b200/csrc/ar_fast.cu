@@ -1,28 +1,49 @@
 // P3 "fast" tier -- the cached AR step as a PDL-chained, CUDA-graph-replayed sequence of sm_100a kernels.
 //
 // Same semantics as ar_engine.cu's exact tier (reference: transformers.py:190-369, attentions.py:60-142), different
-// arithmetic class: bf16 weights / activations / KV cache on tcgen05 (gemm_tc.cu), fp32 residual stream, fp32
-// LayerNorm / softmax / sampler.  What the chain looks like for one transformer block (M = batch rows):
+// arithmetic class: 16-bit weights / activations / KV cache on tcgen05 (gemm_tc.cu) -- fp16 by default, the reference's own
+// autocast class (transformers.py:114,206; main_sampling_fid.py:216), bf16 on request -- fp32 accumulation, fp32 residual
+// stream, fp32 LayerNorm / softmax / sampler.
 //
-//     ln_reduce   x += bias_prev + sum_s partial_prev[s] ; xn = LN(x) (bf16)      <- fused split-K reduction + residual
-//     gemm_tc     qkv partials = Wqkv . xn                                         (split-K, 144 CTAs)
-//     attn_fast   q,k,v = sum partials + bias ; append k,v to the bf16 cache ; softmax(q k^T/8) v -> att (bf16)
-//     gemm_tc     proj partials = Wproj . att
-//     ln_reduce   x += bproj + sum partials ; xn = LN2(x)
-//     gemm_tc     h = gelu(W1 . xn + b1) (bf16)            (direct epilogue, or split-K + act_reduce)
-//     gemm_tc     fc2 partials = W2 . h
+// One transformer block on the single new token of every batch row (M = batch rows):
+//
+//     ln_reduce  x += bias_prev + sum_s partial_prev[s] ; xn = LN(x)     <- fused split-K reduction + residual
+//     gemm_tc    qkv partials = Wqkv . xn                                 (split-K, 144 CTAs)
+//     attn_fast  q,k,v = sum partials + bias ; append k,v to the cache ; softmax(q k^T/8) v -> att
+//     gemm_tc    proj partials = Wproj . att
+//     ln_reduce  x += bproj + sum partials ; xn = LN2(x)
+//     gemm_tc    fc1 partials ; act_reduce h = gelu(sum + b1)
+//     gemm_tc    fc2 partials = W2 . h
+//
+// Every launch is one all-to-all exchange between the SMs (the step is bound by the latency of these
+// dependent exchanges, not by HBM).  Forms with fewer LAUNCHES but the same number of EXCHANGES -- a persistent megakernel with
+// grid barriers (round 1), split-K reduced inside the GEMM behind an arrival counter with LayerNorm folded into the weights
+// (round 2: 5 launches per block) -- were built, parity-tested and measured slower (258 and 249-256 ms against 194 ms per 64
+// images); they are not kept in the tree.
 //
 // Every kernel starts with griddepcontrol.launch_dependents and reads upstream data only after griddepcontrol.wait, so
 // the NEXT kernel's prologue -- for the GEMMs: filling the shared-memory ring with weight tiles -- overlaps this one.
 // Position-dependent scalars (sequence index, spatial index, token counter) live in a device-side StepState that the
-// last kernel of each graph advances, so three captured graphs (cond-token body step, code-token body step, head steps
-// + sampling) are replayed for all positions without host involvement.
+// last kernel of each graph advances, so a handful of captured graphs (cond-token body step, code-token body step, head
+// steps + sampling) are replayed for all positions without host involvement.
+//
+// The prefix (cond tokens, and on a start_loc resume the code tokens before it) is prefilled in ONE pass of M = B*T row
+// GEMMs + a causal attention kernel that writes the KV cache (reference: transformers.py:237-239, attentions.py:60-104 with
+// Tnew > 1); the token-by-token replay of the single-step graph remains available (flag) and is the prefill's oracle.
+#include <algorithm>
+#include <cstring>
+#include <string>
 #include <vector>
 
 #include "kernels.h"
 #include "tc_common.cuh"
 
 namespace rqb {
+
+// diagnostic stage trace: 4 globaltimer stamps per launch written by CTA 0 (entry, dependency resolved, mid, done)
+#define TR_IN(tr)  do { if ((tr) != nullptr && blockIdx.x == 0 && threadIdx.x == 0) (tr)[0] = tc::gtimer(); } while (0)
+#define TR_DEP(tr) do { if ((tr) != nullptr && blockIdx.x == 0 && threadIdx.x == 0) (tr)[1] = tc::gtimer(); } while (0)
+#define TR_OUT(tr) do { if ((tr) != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { (tr)[2] = tc::gtimer(); (tr)[3] = (tr)[2]; } } while (0)
 
 template <typename... KArgs, typename... Args>
 static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
@@ -42,20 +63,22 @@ static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-// x_out = x_in + bias + sum_s partial[s] (+ extra row) ; xn = LayerNorm(x_out) in bf16.  One CTA per batch row.
+// x_out = x_in + bias + sum_s partial[s] (+ extra row) ; xn = LayerNorm(x_out) in 16-bit.  One CTA per row.
 __global__ void __launch_bounds__(384)
 ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int S, const float* __restrict__ bias,
                  const float* __restrict__ extra, float* __restrict__ x_out, const float* __restrict__ g,
-                 const float* __restrict__ be, __nv_bfloat16* __restrict__ xn, int B, int E) {
+                 const float* __restrict__ be, h16* __restrict__ xn, int B, int E, int bf, long long* tr) {
     // each thread owns up to 3 float4 chunks of the row (E <= 384*4*3); every load is issued before the first dependent add and
     // the row stays in registers between the statistics and the normalisation
     __shared__ float red[33];
     tc::pdl_launch_dependents();
+    TR_IN(tr);
     tc::pdl_wait();
+    TR_DEP(tr);
     const int b = blockIdx.x;
     const int E4 = E >> 2;
     const int S12 = S < 12 ? S : 12;
-    float4 v[3];
+    float4 v[3], gg[3], bb[3];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -63,6 +86,7 @@ ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ parti
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e4 < E4) {
             float4 pr[12];
+            if (xn) { gg[k] = reinterpret_cast<const float4*>(g)[e4]; bb[k] = reinterpret_cast<const float4*>(be)[e4]; }
 #pragma unroll
             for (int i = 0; i < 12; i++)
                 if (i < S12) pr[i] = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
@@ -80,38 +104,122 @@ ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ parti
             s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
         }
     }
-    const float mean = block_sum(s, red) / (float)E;
-    float q = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-        if (threadIdx.x + k * 384 < E4) {
-            const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
-            q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
-        }
-    const float rstd = rsqrtf(block_sum(q, red) / (float)E + 1e-5f);
     if (xn) {
+        const float mean = block_sum(s, red) / (float)E;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (threadIdx.x + k * 384 < E4) {
+                const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+                q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+            }
+        const float rstd = rsqrtf(block_sum(q, red) / (float)E + 1e-5f);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const int e4 = threadIdx.x + k * 384;
             if (e4 < E4) {
-                const float4 gg = reinterpret_cast<const float4*>(g)[e4], bb = reinterpret_cast<const float4*>(be)[e4];
-                __nv_bfloat162 h0 = __floats2bfloat162_rn((v[k].x - mean) * rstd * gg.x + bb.x, (v[k].y - mean) * rstd * gg.y + bb.y);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn((v[k].z - mean) * rstd * gg.z + bb.z, (v[k].w - mean) * rstd * gg.w + bb.w);
                 uint2 pk;
-                pk.x = *reinterpret_cast<unsigned*>(&h0);
-                pk.y = *reinterpret_cast<unsigned*>(&h1);
+                pk.x = pack_h16x2((v[k].x - mean) * rstd * gg[k].x + bb[k].x, (v[k].y - mean) * rstd * gg[k].y + bb[k].y, bf);
+                pk.y = pack_h16x2((v[k].z - mean) * rstd * gg[k].z + bb[k].z, (v[k].w - mean) * rstd * gg[k].w + bb[k].w, bf);
                 reinterpret_cast<uint2*>(xn + (int64_t)b * E)[e4] = pk;
             }
         }
     }
+    TR_OUT(tr);
 }
 
-// h = bf16(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K); 4 elements per thread, all partial loads in flight
-__global__ void __launch_bounds__(256)
-act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, __nv_bfloat16* __restrict__ h, int B,
-                  int N) {
+// The same reduction + LayerNorm with each row split over a 2-CTA thread-block cluster (128 CTAs at B = 64 instead of 64: the
+// kernel is bound by one SM pulling S x E x 4 B of partials out of L2).  Each CTA owns half of the features; the halves exchange
+// (mean, M2) once through distributed shared memory and combine them exactly (Chan).  E % 8 == 0, E / 8 <= 3 * 192.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
+ln_reduce2_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int S, const float* __restrict__ bias,
+                  const float* __restrict__ extra, float* __restrict__ x_out, const float* __restrict__ g,
+                  const float* __restrict__ be, h16* __restrict__ xn, int B, int E, int bf, long long* tr) {
+    __shared__ float red[33];
+    __shared__ float xchg[2];
     tc::pdl_launch_dependents();
+    TR_IN(tr);
     tc::pdl_wait();
+    TR_DEP(tr);
+    const int b = blockIdx.x >> 1, rank = blockIdx.x & 1;
+    const int E4h = E >> 3, base4 = rank * E4h;          // float4 chunks per half
+    const int S12 = S < 12 ? S : 12;
+    float4 v[3], gg[3], bb[3];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int i4 = threadIdx.x + k * 192, e4 = base4 + i4;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < E4h) {
+            float4 pr[12];
+            if (xn) { gg[k] = reinterpret_cast<const float4*>(g)[e4]; bb[k] = reinterpret_cast<const float4*>(be)[e4]; }
+#pragma unroll
+            for (int i = 0; i < 12; i++)
+                if (i < S12) pr[i] = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
+            if (x_in) v[k] = reinterpret_cast<const float4*>(x_in + (int64_t)b * E)[e4];
+            if (bias) { float4 t = reinterpret_cast<const float4*>(bias)[e4]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
+#pragma unroll
+            for (int i = 0; i < 12; i++)
+                if (i < S12) { v[k].x += pr[i].x; v[k].y += pr[i].y; v[k].z += pr[i].z; v[k].w += pr[i].w; }
+            for (int i = 12; i < S; i++) {
+                float4 p0 = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
+                v[k].x += p0.x; v[k].y += p0.y; v[k].z += p0.z; v[k].w += p0.w;
+            }
+            if (extra) { float4 t = reinterpret_cast<const float4*>(extra)[e4]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
+            if (x_out) reinterpret_cast<float4*>(x_out + (int64_t)b * E)[e4] = v[k];
+            s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+    }
+    if (xn) {                                             // (uniform over the cluster: both halves take the same branch)
+        const float nh = (float)(E >> 1);
+        const float lmean = block_sum(s, red) / nh;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (threadIdx.x + k * 192 < E4h) {
+                const float d0 = v[k].x - lmean, d1 = v[k].y - lmean, d2 = v[k].z - lmean, d3 = v[k].w - lmean;
+                q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+            }
+        const float lm2 = block_sum(q, red);
+        if (threadIdx.x == 0) { xchg[0] = lmean; xchg[1] = lm2; }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        uint32_t peer;
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(tc::smem_u32(xchg)), "r"((uint32_t)(rank ^ 1)));
+        float pmean, pm2;
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pmean) : "r"(peer) : "memory");
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pm2) : "r"(peer + 4) : "memory");
+        // combine in a rank-independent order so that both halves compute the same statistics bit for bit
+        const float m_lo = rank == 0 ? lmean : pmean, m_hi = rank == 0 ? pmean : lmean;
+        const float q_lo = rank == 0 ? lm2 : pm2, q_hi = rank == 0 ? pm2 : lm2;
+        const float mean = 0.5f * (m_lo + m_hi);
+        const float dl = m_hi - m_lo;
+        const float rstd = rsqrtf(((q_lo + q_hi) + dl * dl * (0.5f * nh)) / (float)E + 1e-5f);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int i4 = threadIdx.x + k * 192, e4 = base4 + i4;
+            if (i4 < E4h) {
+                uint2 pk;
+                pk.x = pack_h16x2((v[k].x - mean) * rstd * gg[k].x + bb[k].x, (v[k].y - mean) * rstd * gg[k].y + bb[k].y, bf);
+                pk.y = pack_h16x2((v[k].z - mean) * rstd * gg[k].z + bb[k].z, (v[k].w - mean) * rstd * gg[k].w + bb[k].w, bf);
+                reinterpret_cast<uint2*>(xn + (int64_t)b * E)[e4] = pk;
+            }
+        }
+        // the peer may still be reading this CTA's exchange slot
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    TR_OUT(tr);
+}
+
+// h = 16-bit(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K); 4 elements per thread, all partial loads in flight
+__global__ void __launch_bounds__(256)
+act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, h16* __restrict__ h, int B, int N, int bf,
+                  long long* tr) {
+    tc::pdl_launch_dependents();
+    TR_IN(tr);
+    tc::pdl_wait();
+    TR_DEP(tr);
     const int64_t total4 = (int64_t)B * N / 4;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256) {
         const int n = (int)((i * 4) % N);
@@ -130,39 +238,56 @@ act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restr
         float r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) r[k] = 0.5f * r[k] * (1.0f + erff(r[k] * 0.70710678118654752440f));
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(r[0], r[1]), h1 = __floats2bfloat162_rn(r[2], r[3]);
         uint2 pk;
-        pk.x = *reinterpret_cast<unsigned*>(&h0);
-        pk.y = *reinterpret_cast<unsigned*>(&h1);
+        pk.x = pack_h16x2(r[0], r[1], bf);
+        pk.y = pack_h16x2(r[2], r[3], bf);
         *reinterpret_cast<uint2*>(h + i * 4) = pk;
     }
+    TR_OUT(tr);
 }
 
-// one warp per (b, head): reduce the split-K qkv partials (+bias), append k,v at row t of the bf16 cache, attend.
+// one warp per (b, head): reduce the split-K qkv partials (+bias), append k,v at row t of the 16-bit cache, attend.
 // lane <-> dims (2*lane, 2*lane+1) for q/k/v/out; lane <-> key for the scores (q and the probabilities are
 // broadcast through shared memory).  T <= 512.
+// The cached rows [0, t) were written by EARLIER graph replays, so they do not depend on the upstream kernel of the chain:
+// with early_t the warp pulls them into L2 before griddepcontrol.wait (the step reads ~0.5 GB of KV per position -- more than
+// L2 holds across a position -- so they would otherwise come from HBM behind two dependent round trips), and after the wait
+// every K row of a 64-key pass / every V row of a 64-row pass is in flight at once.
 constexpr int AF_MAXT = 512;
 __global__ void __launch_bounds__(128)
-attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, __nv_bfloat16* __restrict__ kc,
-                 __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ att, int B, int E, int nh, int Tmax,
-                 const int* __restrict__ t_ptr, int t_host, const float2* __restrict__ stats_in, int nst,
-                 const float* __restrict__ cqkv) {
-    __shared__ float qs[4][64];
-    __shared__ float ps[4][AF_MAXT];
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
+attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, h16* __restrict__ kc, h16* __restrict__ vc,
+                 h16* __restrict__ att, int B, int E, int nh, int Tmax, const int* __restrict__ t_ptr, int t_host, int early_t,
+                 int bf, long long* tr) {
+    extern __shared__ float af_smem[];              // qs[4][64] | ps[4][tp]
+    const int tp = (Tmax + 31) & ~31;
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    float* qs = af_smem + wq * 64;
+    float* ps = af_smem + 4 * 64 + wq * tp;
+    tc::pdl_launch_dependents();
+    TR_IN(tr);
     const int bh = blockIdx.x * 4 + wq;
-    if (bh >= B * nh) return;
-    const int b = bh / nh, h = bh % nh;
-    const int t = t_ptr ? *t_ptr : t_host;
+    const bool valid = bh < B * nh;
+    const int b = valid ? bh / nh : 0, h = valid ? bh % nh : 0;
+    h16* kb = kc + ((int64_t)(b * nh + h) * Tmax) * 64;
+    h16* vb = vc + ((int64_t)(b * nh + h) * Tmax) * 64;
+    int t = 0;
+    if (early_t) {
+        // (position counters are only advanced by the LAST kernel of a graph; no kernel upstream of this one in the graph writes them)
+        t = t_ptr ? *reinterpret_cast<const volatile int*>(t_ptr) : t_host;
+        if (valid)
+            for (int j = lane; j < t; j += 32) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (int64_t)j * 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (int64_t)j * 64));
+            }
+    }
+    tc::pdl_wait();
+    TR_DEP(tr);
+    if (!early_t) t = t_ptr ? *t_ptr : t_host;
+    if (valid) {
     const int c = h * 64 + 2 * lane;
-    // stats_in != NULL: the qkv GEMM ran on the raw residual rows with LayerNorm folded into its weights (rqb200_block_weights
-    // .cqkv); the row statistics are applied here: q = rstd*(sum - mean*c) + b'
-    const bool fold = stats_in != nullptr;
-    float2 q = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[c], bqkv[c + 1]);
-    float2 k = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[E + c], bqkv[E + c + 1]);
-    float2 v = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[2 * E + c], bqkv[2 * E + c + 1]);
+    float2 q = make_float2(bqkv[c], bqkv[c + 1]);
+    float2 k = make_float2(bqkv[E + c], bqkv[E + c + 1]);
+    float2 v = make_float2(bqkv[2 * E + c], bqkv[2 * E + c + 1]);
 #pragma unroll 4
     for (int s = 0; s < S; s++) {
         const float* p = part + ((int64_t)s * B + b) * 3 * E;
@@ -171,59 +296,67 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
         float2 cc = *reinterpret_cast<const float2*>(p + 2 * E + c);
         q.x += a.x; q.y += a.y; k.x += bb.x; k.y += bb.y; v.x += cc.x; v.y += cc.y;
     }
-    if (fold) {
-        float s1 = 0.f;
-        for (int i = lane; i < nst; i += 32) s1 += __ldcg(stats_in + (int64_t)b * nst + i).x;
-        const float mean = warp_sum(s1) / (float)E;
-        float m2 = 0.f;
-        for (int i = lane; i < nst; i += 32) {
-            const float2 st = __ldcg(stats_in + (int64_t)b * nst + i);
-            const float d = st.x * (1.0f / 128.0f) - mean;
-            m2 += st.y + 128.0f * d * d;
-        }
-        const float rstd = rsqrtf(warp_sum(m2) / (float)E + 1e-5f);
-        q.x = rstd * (q.x - mean * cqkv[c]) + bqkv[c];
-        q.y = rstd * (q.y - mean * cqkv[c + 1]) + bqkv[c + 1];
-        k.x = rstd * (k.x - mean * cqkv[E + c]) + bqkv[E + c];
-        k.y = rstd * (k.y - mean * cqkv[E + c + 1]) + bqkv[E + c + 1];
-        v.x = rstd * (v.x - mean * cqkv[2 * E + c]) + bqkv[2 * E + c];
-        v.y = rstd * (v.y - mean * cqkv[2 * E + c + 1]) + bqkv[2 * E + c + 1];
-    }
-    __nv_bfloat16* kb = kc + ((int64_t)(b * nh + h) * Tmax) * 64;
-    __nv_bfloat16* vb = vc + ((int64_t)(b * nh + h) * Tmax) * 64;
-    const __nv_bfloat162 k2 = __floats2bfloat162_rn(k.x, k.y), v2 = __floats2bfloat162_rn(v.x, v.y);
-    *reinterpret_cast<__nv_bfloat162*>(kb + (int64_t)t * 64 + 2 * lane) = k2;
-    *reinterpret_cast<__nv_bfloat162*>(vb + (int64_t)t * 64 + 2 * lane) = v2;
-    // use the bf16-rounded q/k/v everywhere (what a later step reads back from the cache)
-    const float2 qf = __bfloat1622float2(__floats2bfloat162_rn(q.x, q.y)), kf = __bfloat1622float2(k2), vf = __bfloat1622float2(v2);
-    qs[wq][2 * lane] = qf.x;
-    qs[wq][2 * lane + 1] = qf.y;
+    const uint32_t k2 = pack_h16x2(k.x, k.y, bf), v2 = pack_h16x2(v.x, v.y, bf);
+    *reinterpret_cast<uint32_t*>(kb + (int64_t)t * 64 + 2 * lane) = k2;
+    *reinterpret_cast<uint32_t*>(vb + (int64_t)t * 64 + 2 * lane) = v2;
+    // use the 16-bit-rounded q/k/v everywhere (what a later step reads back from the cache)
+    const float2 qf = unpack_h16x2(pack_h16x2(q.x, q.y, bf), bf), kf = unpack_h16x2(k2, bf), vf = unpack_h16x2(v2, bf);
+    qs[2 * lane] = qf.x;
+    qs[2 * lane + 1] = qf.y;
     __syncwarp();
     const float s_new = warp_sum(qf.x * kf.x + qf.y * kf.y) * 0.125f;
     float m = s_new;
-    for (int j = lane; j < t; j += 32) {          // scores of the cached rows
-        const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)j * 64);
-        float acc = 0.f;
+    for (int j0 = 0; j0 < t; j0 += 64) {          // scores of the cached rows: two rows per lane, 16 x 16 B in flight
+        const int ja = j0 + lane, jb = j0 + 32 + lane;
+        uint4 wa[8], wb[8];
+        if (ja < t) {
+            const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)ja * 64);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            uint4 w = kr[u];
-            const __nv_bfloat162* kp = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-            for (int z = 0; z < 4; z++) {
-                float2 kk = __bfloat1622float2(kp[z]);
-                acc = fmaf(qs[wq][(u * 4 + z) * 2], kk.x, acc);
-                acc = fmaf(qs[wq][(u * 4 + z) * 2 + 1], kk.y, acc);
-            }
+            for (int u = 0; u < 8; u++) wa[u] = kr[u];
         }
-        acc *= 0.125f;
-        ps[wq][j] = acc;
-        m = fmaxf(m, acc);
+        if (jb < t) {
+            const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)jb * 64);
+#pragma unroll
+            for (int u = 0; u < 8; u++) wb[u] = kr[u];
+        }
+        if (ja < t) {
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t* kp = reinterpret_cast<const uint32_t*>(&wa[u]);
+#pragma unroll
+                for (int z = 0; z < 4; z++) {
+                    const float2 kk = unpack_h16x2(kp[z], bf);
+                    acc = fmaf(qs[(u * 4 + z) * 2], kk.x, acc);
+                    acc = fmaf(qs[(u * 4 + z) * 2 + 1], kk.y, acc);
+                }
+            }
+            acc *= 0.125f;
+            ps[ja] = acc;
+            m = fmaxf(m, acc);
+        }
+        if (jb < t) {
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t* kp = reinterpret_cast<const uint32_t*>(&wb[u]);
+#pragma unroll
+                for (int z = 0; z < 4; z++) {
+                    const float2 kk = unpack_h16x2(kp[z], bf);
+                    acc = fmaf(qs[(u * 4 + z) * 2], kk.x, acc);
+                    acc = fmaf(qs[(u * 4 + z) * 2 + 1], kk.y, acc);
+                }
+            }
+            acc *= 0.125f;
+            ps[jb] = acc;
+            m = fmaxf(m, acc);
+        }
     }
     m = warp_max(m);
     float sum = 0.f;
     for (int j = lane; j < t; j += 32) {
-        float e = __expf(ps[wq][j] - m);
-        ps[wq][j] = e;
+        float e = __expf(ps[j] - m);
+        ps[j] = e;
         sum += e;
     }
     const float e_new = __expf(s_new - m);
@@ -231,93 +364,117 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     __syncwarp();
     const float inv = 1.0f / sum;
     float2 o = make_float2(e_new * vf.x, e_new * vf.y);
-    int j = 0;
-    for (; j + 16 <= t; j += 16) {                        // 16 independent V rows in flight
-        __nv_bfloat162 raw[16];
+    for (int j0 = 0; j0 < t; j0 += 64) {                  // up to 64 V rows in flight (rows added in cache order: same sum order)
+        uint32_t raw[64];
 #pragma unroll
-        for (int u = 0; u < 16; u++) raw[u] = *reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)(j + u) * 64 + 2 * lane);
+        for (int u = 0; u < 64; u++)
+            raw[u] = (j0 + u < t) ? *reinterpret_cast<const uint32_t*>(vb + (int64_t)(j0 + u) * 64 + 2 * lane) : 0u;
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-            const float2 vv = __bfloat1622float2(raw[u]);
-            o.x = fmaf(ps[wq][j + u], vv.x, o.x);
-            o.y = fmaf(ps[wq][j + u], vv.y, o.y);
-        }
+        for (int u = 0; u < 64; u++)
+            if (j0 + u < t) {
+                const float2 vv = unpack_h16x2(raw[u], bf);
+                o.x = fmaf(ps[j0 + u], vv.x, o.x);
+                o.y = fmaf(ps[j0 + u], vv.y, o.y);
+            }
     }
-    for (; j + 4 <= t; j += 4) {
-        __nv_bfloat162 raw[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) raw[u] = *reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)(j + u) * 64 + 2 * lane);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const float2 vv = __bfloat1622float2(raw[u]);
-            o.x = fmaf(ps[wq][j + u], vv.x, o.x);
-            o.y = fmaf(ps[wq][j + u], vv.y, o.y);
-        }
+    *reinterpret_cast<uint32_t*>(att + (int64_t)b * E + c) = pack_h16x2(o.x * inv, o.y * inv, bf);
     }
-    for (; j < t; j++) {
-        const float p = ps[wq][j];
-        float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)j * 64 + 2 * lane));
-        o.x = fmaf(p, vv.x, o.x);
-        o.y = fmaf(p, vv.y, o.y);
-    }
-    *reinterpret_cast<__nv_bfloat162*>(att + (int64_t)b * E + c) = __floats2bfloat162_rn(o.x * inv, o.y * inv);
+    TR_OUT(tr);
 }
 
-// RQB200_GR chain with folded LayerNorm: x_out = x_in (+ extra row); xq = bf16(x_out); stats[b][tile] = (sum, M2 about the tile
-// mean) for every 128-feature tile -- what the GT_GR epilogue of proj / fc2 emits for all later layers.  One CTA per batch row,
-// warp <-> tile, lane <-> 4 features.
-__global__ void __launch_bounds__(384)
-row_prep_kernel(const float* __restrict__ x_in, const float* __restrict__ extra, float* __restrict__ x_out,
-                __nv_bfloat16* __restrict__ xq, float2* __restrict__ stats, int B, int E) {
+// Causal attention over a whole prefix in one launch (batched prefill / teacher-forced forward).  qkv [M, 3E] 16-bit (bias already
+// added by the GEMM epilogue), row of (group g, token t) = t * G + g  (token-major: the rows of one token are contiguous, like the
+// single-step buffers).  One CTA per (group, head); the group's K and V rows are staged in shared memory (row stride 66 elements:
+// conflict-free for lane <-> key), warp <-> query, lane <-> key for the scores and lane <-> 2 dims for the output -- the same
+// arithmetic order as attn_fast_kernel's.  When kc != NULL the K / V rows are also written to the cache [g][head][t][64].
+constexpr int PA_MAXT = 128;
+__global__ void __launch_bounds__(128)
+prefill_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ kc, h16* __restrict__ vc, h16* __restrict__ att, int G, int T, int E,
+                    int nh, int Tmax, int bf) {
+    __shared__ uint32_t ks[PA_MAXT][33], vs[PA_MAXT][33];
+    __shared__ float qs[4][64];
+    __shared__ float ps[4][PA_MAXT];
     tc::pdl_launch_dependents();
     tc::pdl_wait();
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nt = E / 128;
-    for (int t = warp; t < nt; t += nw) {
-        const int e = t * 128 + 4 * lane;
-        float4 v = *reinterpret_cast<const float4*>(x_in + (int64_t)b * E + e);
-        if (extra) { const float4 a = *reinterpret_cast<const float4*>(extra + e); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
-        if (x_out) *reinterpret_cast<float4*>(x_out + (int64_t)b * E + e) = v;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<unsigned*>(&h0);
-        pk.y = *reinterpret_cast<unsigned*>(&h1);
-        *reinterpret_cast<uint2*>(xq + (int64_t)b * E + e) = pk;
-        const float s1 = warp_sum((v.x + v.y) + (v.z + v.w));
-        const float tm = s1 * (1.0f / 128.0f);
-        const float d0 = v.x - tm, d1 = v.y - tm, d2 = v.z - tm, d3 = v.w - tm;
-        const float m2 = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
-        if (lane == 0) stats[(int64_t)b * nt + t] = make_float2(s1, m2);
+    const int g = blockIdx.x / nh, h = blockIdx.x % nh;
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < T * 32; i += 128) {
+        const int t = i >> 5, c2 = i & 31;
+        const h16* row = qkv + ((int64_t)t * G + g) * 3 * E + h * 64 + 2 * c2;
+        const uint32_t kk = *reinterpret_cast<const uint32_t*>(row + E), vv = *reinterpret_cast<const uint32_t*>(row + 2 * E);
+        ks[t][c2] = kk;
+        vs[t][c2] = vv;
+        if (kc) {
+            *reinterpret_cast<uint32_t*>(kc + (((int64_t)g * nh + h) * Tmax + t) * 64 + 2 * c2) = kk;
+            *reinterpret_cast<uint32_t*>(vc + (((int64_t)g * nh + h) * Tmax + t) * 64 + 2 * c2) = vv;
+        }
     }
-}
-// arrival counters of the GT_GR GEMMs of one graph: zeroed by the graph's last-but-one kernel for its next replay
-__global__ void __launch_bounds__(256) ctr_zero_kernel(unsigned* __restrict__ ctr, int n) {
-    tc::pdl_launch_dependents();
-    tc::pdl_wait();
-    for (int i = threadIdx.x; i < n; i += 256) ctr[i] = 0u;
+    __syncthreads();
+    for (int t = wq; t < T; t += 4) {
+        const float2 qf = unpack_h16x2(*reinterpret_cast<const uint32_t*>(qkv + ((int64_t)t * G + g) * 3 * E + h * 64 + 2 * lane), bf);
+        __syncwarp();
+        qs[wq][2 * lane] = qf.x;
+        qs[wq][2 * lane + 1] = qf.y;
+        __syncwarp();
+        float m = -INFINITY;
+        for (int j = lane; j <= t; j += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                const float2 kk = unpack_h16x2(ks[j][u], bf);
+                acc = fmaf(qs[wq][2 * u], kk.x, acc);
+                acc = fmaf(qs[wq][2 * u + 1], kk.y, acc);
+            }
+            acc *= 0.125f;
+            ps[wq][j] = acc;
+            m = fmaxf(m, acc);
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j <= t; j += 32) {
+            const float e = __expf(ps[wq][j] - m);
+            ps[wq][j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        float2 o = make_float2(0.f, 0.f);
+        for (int j = 0; j <= t; j++) {
+            const float2 vv = unpack_h16x2(vs[j][lane], bf);
+            o.x = fmaf(ps[wq][j], vv.x, o.x);
+            o.y = fmaf(ps[wq][j], vv.y, o.y);
+        }
+        const float inv = 1.0f / sum;
+        *reinterpret_cast<uint32_t*>(att + ((int64_t)t * G + g) * E + h * 64 + 2 * lane) = pack_h16x2(o.x * inv, o.y * inv, bf);
+    }
 }
 
 // token sources --------------------------------------------------------------------------------------------------
 // cond token s: x[b,:] = cond_emb[cond[b,s]] + pos_emb_cond[s]                      (transformers.py:224)
+// grid (B, n_tokens): token s = stt->s + blockIdx.y, written to row blockIdx.y * B + b
 __global__ void __launch_bounds__(256)
 cond_tok_kernel(const StepState* __restrict__ stt, const float* __restrict__ cond_emb, const float* __restrict__ pos_cond,
                 int cond_len, int vocab_cond, int E, float* __restrict__ x) {
     tc::pdl_launch_dependents();
     tc::pdl_wait();
-    const int b = blockIdx.x, s = stt->s;
+    const int b = blockIdx.x, s = stt->s + blockIdx.y, B = gridDim.x;
     int64_t c = stt->cond ? stt->cond[(int64_t)b * cond_len + s] : 0;
     c = c < 0 ? 0 : (c >= vocab_cond ? vocab_cond - 1 : c);
-    for (int e = threadIdx.x; e < E; e += 256) x[(int64_t)b * E + e] = cond_emb[c * E + e] + pos_cond[(int64_t)s * E + e];
+    float* xr = x + ((int64_t)blockIdx.y * B + b) * E;
+    for (int e = threadIdx.x; e < E; e += 256) xr[e] = cond_emb[c * E + e] + pos_cond[(int64_t)s * E + e];
 }
-// summed code embeddings in bf16: mode 0 -> all D codes of position idx-1 (body input), mode d>=1 -> codes 0..d-1 of
+// summed code embeddings in 16-bit: mode 0 -> all D codes of position idx-1 (body input), mode d>=1 -> codes 0..d-1 of
 // position idx (head input, cumsum)                                              (transformers.py:219-225, 250-255)
+// mode < 0 (prefill / forward): grid (B, n_pos); all D codes of position blockIdx.y + pos0, written to row blockIdx.y * B + b
 __global__ void __launch_bounds__(64)
-code_sum_kernel(const StepState* __restrict__ stt, const float* __restrict__ cb, int HW, int D, int K, int C, int mode,
-                __nv_bfloat16* __restrict__ out) {
+code_sum_kernel(const StepState* __restrict__ stt, const float* __restrict__ cb, int HW, int D, int K, int C, int mode, int pos0,
+                h16* __restrict__ out, int bf) {
     tc::pdl_launch_dependents();
     tc::pdl_wait();
-    const int b = blockIdx.x;
-    const int pos = mode == 0 ? stt->idx - 1 : stt->idx;
-    const int nd = mode == 0 ? D : mode;
+    const int b = blockIdx.x, B = gridDim.x;
+    const int pos = mode < 0 ? pos0 + blockIdx.y : (mode == 0 ? stt->idx - 1 : stt->idx);
+    const int nd = mode <= 0 ? D : mode;
+    h16* o = out + ((int64_t)blockIdx.y * B + b) * C;
     for (int c = threadIdx.x; c < C; c += 64) {
         float a = 0.f;
         for (int i = 0; i < nd; i++) {
@@ -325,7 +482,7 @@ code_sum_kernel(const StepState* __restrict__ stt, const float* __restrict__ cb,
             k = k < 0 ? 0 : (k >= K ? K - 1 : k);
             a += cb[k * C + c];
         }
-        out[(int64_t)b * C + c] = __float2bfloat16(a);
+        o[c] = pack_h16(a, bf);
     }
 }
 // bookkeeping: which graph just ran decides what advances
@@ -343,8 +500,12 @@ __global__ void __launch_bounds__(256) logits_copy_kernel(const StepState* __res
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) dst[i] = lg[i];
 }
 
-__global__ void init_state_kernel(StepState* dst, StepState v) {
-    if (threadIdx.x == 0) *dst = v;
+// keep_pos != 0: a resumed span keeps the position counters the previous span left behind
+__global__ void init_state_kernel(StepState* dst, StepState v, int keep_pos) {
+    if (threadIdx.x == 0) {
+        if (keep_pos) { v.s = dst->s; v.idx = dst->idx; }
+        *dst = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ engine
@@ -352,60 +513,62 @@ struct FastLayer {
     CUtensorMap qkv, proj, fc1, fc2;
 };
 
+enum { G_COND = 0, G_CODE = 1, G_HEAD = 2, G_HEAD_LOGITS = 3, G_COUNT = 4 };
+
 struct ArFast {
     rqb200_ar_config cfg;
     rqb200_ar_weights w;
     std::vector<rqb200_block_weights> body, head;
     std::vector<FastLayer> lbody, lhead;
     CUtensorMap tm_win, tm_whead, tm_cls;
+    int bf = 0;                          // 16-bit format: 0 fp16, 1 bf16
     // per (workspace, B) state
     void* ws_base = nullptr;
     int B = 0;
-    CUtensorMap tx_xn, tx_att, tx_h, tx_s, tx_xq;
-    cudaGraphExec_t g_cond = nullptr, g_code = nullptr, g_head = nullptr;
-    int64_t n_nodes[3] = {0, 0, 0};      // kernels recorded in each graph (for the launch counter)
+    CUtensorMap tx_xn, tx_att, tx_h, tx_s;
+    cudaGraphExec_t graphs[G_COUNT] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t n_nodes[G_COUNT] = {0, 0, 0, 0};   // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
-    bool use_graph = true, use_pdl = true;
+    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, next_pf = true, ln_cluster = false;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
-    // persistent ("mega") form: phase programs living in the workspace
-    bool want_mega = false, use_mega = false;   // opt-in (RQB200_MEGA=1): measured slower than the PDL chain so far, see DESIGN.md
-    int mega_split_fc1 = 3;
-    // cluster (DSMEM) split-K for proj / fc1 / fc2: the GEMM itself emits x += ..., h = gelu(...) -- no partial round trip
-    bool w_tiled = false;        // weights packed tile-major by the host binding (cfg.weight_layout)
-    int skip = 0;                // diagnostics only (RQB200_SKIP bitmask): drop a kernel type from the chain to measure its in-situ cost
-    bool cluster = false;        // all of proj/fc1/fc2 (measured slower than split-K partials + fused LN reduction: 289 vs 243 ms)
-    bool fc1_cluster = false;    // fc1 only (RQB200_FC1_CLUSTER=2|3|4): also slower (311-319 ms) -- cluster launches cost more than they save here
-    int cl_proj = 8, cl_fc1 = 2, cl_fc2 = 8;
-    // RQB200_GR=1 (experiment for the next round): proj / fc1 / fc2 reduce their split-K partials inside the GEMM (GT_GR), so a block
-    // is ln, qkv, attn, proj, ln, fc1, fc2 (7 launches); with LayerNorm folded into the weights (rqb200_block_weights.cqkv / .c1)
-    // it is qkv, attn, proj, fc1, fc2 (5 launches).  Needs every GT_GR grid co-resident and the GPU to itself.
-    bool gr = false, fold = false;
-    mutable int ctr_next = 0;    // next free arrival counter while a chain is being recorded
     int n_sm = 148;
-    MegaParams prog_cond = {}, prog_code = {}, prog_head[8] = {};
+    // diagnostic stage trace (cfg.flags & RQB200_AR_TRACE)
+    bool trace = false;
+    mutable long long* tr_base = nullptr;
+    mutable int tr_next = 0;
+    mutable std::vector<std::string> tr_names;
+    int tr_graph_base[G_COUNT + 1] = {0, 0, 0, 0, 0};
 };
+
+constexpr int TR_CAP = 4096;             // launches per trace buffer
 
 struct FastWs {
     StepState* state;
-    MPhase* tables;
-    unsigned* bar;
     long long* trace;
     float *XB, *XH, *P, *LOGITS;
-    __nv_bfloat16 *XN, *ATT, *Hh, *S;
-    __nv_bfloat16 *kc_body, *vc_body, *kc_head, *vc_head;
-    // RQB200_GR chain
-    unsigned* ctr;               // one arrival counter per output tile of every GT_GR GEMM of a graph
-    int ctr_cap;
-    __nv_bfloat16* XQ;           // bf16 copy of the residual rows (folded LayerNorm: the qkv / fc1 operand)
-    float2* ST;                  // [B][E/128] tile statistics of the residual rows
+    h16 *XN, *ATT, *Hh, *S;
+    h16 *kc_body, *vc_body, *kc_head, *vc_head;
+    // batched prefill (M = B * T rows, token-major)
+    int64_t Mmax;
+    float* PX;                   // [Mmax, E] residual stream
+    h16 *PXN, *PQKV, *PATT, *PH, *PS;
 };
 
-static int pick_split(int n_tiles, int nkb, int want) {
-    int s = want > 0 ? want : 148 / n_tiles;
+static int pick_split(int n_tiles, int nkb, int want, int n_sm) {
+    int s = want > 0 ? want : n_sm / n_tiles;
     if (s < 1) s = 1;
     if (s > nkb) s = nkb;
     return s;
 }
+
+static long long* tr_slot(const ArFast& f, const char* name) {
+    if (!f.trace || !f.tr_base || f.tr_next >= TR_CAP) return nullptr;
+    if ((int)f.tr_names.size() <= f.tr_next) f.tr_names.resize(f.tr_next + 1);
+    f.tr_names[f.tr_next] = name;
+    return f.tr_base + 4 * (int64_t)(f.tr_next++);
+}
+
+static int prefill_tmax(const rqb200_ar_config& c) { return std::min(PA_MAXT, c.cond_len + c.H * c.W - 1); }
 
 static size_t fast_layout(const ArFast& f, int B, void* base, size_t cap, FastWs* ws) {
     const rqb200_ar_config& c = f.cfg;
@@ -413,256 +576,127 @@ static size_t fast_layout(const ArFast& f, int B, void* base, size_t cap, FastWs
     const int64_t E = c.embed_dim, HW = (int64_t)c.H * c.W, Tb = c.cond_len + HW;
     FastWs w;
     w.state = a.take<StepState>(1);
-    w.bar = a.take<unsigned>(64);
-    w.trace = a.take<long long>(4096);
-    w.tables = a.take<MPhase>((size_t)(8 * c.n_body) * 2 + 2 + (size_t)c.D * (4 + 8 * c.n_head_layers) + 8);
+    w.trace = a.take<long long>(4 * TR_CAP);
     w.XB = a.take<float>(B * E);
     w.XH = a.take<float>(B * E);
-    int maxs = std::max(std::max(f.split_qkv * 3, f.split_proj), std::max(f.split_fc2, std::max(f.split_fc1, f.mega_split_fc1) * 4));
+    int maxs = std::max(std::max(f.split_qkv * 3, f.split_proj), std::max(f.split_fc2, f.split_fc1 * 4));
     w.P = a.take<float>((int64_t)maxs * B * E);
     w.LOGITS = a.take<float>((int64_t)B * c.vocab);
-    w.XN = a.take<__nv_bfloat16>(B * E);
-    w.ATT = a.take<__nv_bfloat16>(B * E);
-    w.Hh = a.take<__nv_bfloat16>(B * 4 * E);
-    w.S = a.take<__nv_bfloat16>((int64_t)B * c.code_dim);
-    w.ctr_cap = (int)(std::max<int64_t>(c.n_body, (int64_t)c.D * c.n_head_layers) * (6 * E / 128));
-    w.ctr = a.take<unsigned>(w.ctr_cap);
-    w.XQ = a.take<__nv_bfloat16>(B * E);
-    w.ST = a.take<float2>(B * (E / 128));
+    w.XN = a.take<h16>(B * E);
+    w.ATT = a.take<h16>(B * E);
+    w.Hh = a.take<h16>(B * 4 * E);
+    w.S = a.take<h16>((int64_t)B * c.code_dim);
     const int64_t per_body = (int64_t)B * c.n_head * Tb * 64, per_head = (int64_t)B * c.n_head * c.D * 64;
-    w.kc_body = a.take<__nv_bfloat16>(per_body * c.n_body);
-    w.vc_body = a.take<__nv_bfloat16>(per_body * c.n_body);
-    w.kc_head = a.take<__nv_bfloat16>(per_head * c.n_head_layers);
-    w.vc_head = a.take<__nv_bfloat16>(per_head * c.n_head_layers);
+    w.kc_body = a.take<h16>(per_body * c.n_body);
+    w.vc_body = a.take<h16>(per_body * c.n_body);
+    w.kc_head = a.take<h16>(per_head * c.n_head_layers);
+    w.vc_head = a.take<h16>(per_head * c.n_head_layers);
+    w.Mmax = f.batched_prefill ? (int64_t)B * prefill_tmax(c) : 0;
+    w.PX = a.take<float>(w.Mmax * E);
+    w.PXN = a.take<h16>(w.Mmax * E);
+    w.PQKV = a.take<h16>(w.Mmax * 3 * E);
+    w.PATT = a.take<h16>(w.Mmax * E);
+    w.PH = a.take<h16>(w.Mmax * 4 * E);
+    w.PS = a.take<h16>(w.Mmax * c.code_dim);
     if (ws) *ws = w;
     return a.off + 256;
 }
 
-static int gemm(const ArFast& f, const CUtensorMap& tw, const CUtensorMap& tx, int N_out, int K, int B, int splits, int mode,
-                const float* bias, float bias_scale, void* out, float* partial, const float* residual, int64_t ld_res,
-                const int* res_row_ptr, int64_t res_row_stride, cudaStream_t st) {
+static GemmTcParams gemm_base(const ArFast& f, int N_out, int K, int rows, int splits, int mode) {
     GemmTcParams p = {};
-    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits; p.mode = mode;
-    p.bias = bias; p.bias_scale = bias_scale; p.out = out; p.ld_out = N_out; p.partial = partial;
+    p.N_out = N_out; p.K = K; p.B = rows; p.splits = splits; p.mode = mode;
+    p.fmt = f.bf; p.deep = f.deep ? 1 : 0; p.l2pf = f.l2pf ? 1 : 0; p.bias_scale = 1.f; p.ld_out = N_out;
+    return p;
+}
+
+static int gemm(const ArFast& f, const char* name, const CUtensorMap& tw, const CUtensorMap& tx, int N_out, int K, int B, int splits,
+                int mode, const float* bias, float bias_scale, void* out, float* partial, const float* residual, int64_t ld_res,
+                const int* res_row_ptr, int64_t res_row_stride, cudaStream_t st, const void* next_w = nullptr,
+                int64_t next_w_bytes = 0) {
+    GemmTcParams p = gemm_base(f, N_out, K, B, splits, mode);
+    p.next_w = f.next_pf ? next_w : nullptr; p.next_w_bytes = next_w_bytes;
+    p.bias = bias; p.bias_scale = bias_scale; p.out = out; p.partial = partial;
     p.residual = residual; p.ld_res = ld_res; p.res_row_ptr = res_row_ptr; p.res_row_stride = res_row_stride;
-    p.w_tiled = f.w_tiled ? 1 : 0;
+    p.trace = tr_slot(f, name);
     return launch_gemm_tc(tw, tx, p, f.use_pdl, st);
 }
 
-// split-K GEMM with the in-kernel group reduction (GT_GR).  kind 0: out f32 = sum + bias + residual (+ bf16 copy + tile statistics);
-// kind 1: out bf16 = gelu(sum + bias), optionally with the folded LayerNorm of the input rows (stats_in, fold_c).
-static int gemm_gr(const ArFast& f, FastWs& ws, const CUtensorMap& tw, const CUtensorMap& tx, int N_out, int K, int B, int splits,
-                   int kind, const float* bias, void* out, int64_t ld_out, const float* residual, void* out_bf16, float2* stats_out,
-                   const float2* stats_in, const float* fold_c, cudaStream_t st) {
-    const int tiles = N_out / 128;
-    if (f.ctr_next + tiles > ws.ctr_cap) return fail(RQB200_EINVAL, "ar fast tier: out of GT_GR arrival counters");
-    GemmTcParams p = {};
-    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits; p.mode = GT_GR;
-    p.bias = bias; p.bias_scale = 1.f; p.out = out; p.ld_out = ld_out;
-    p.residual = residual; p.ld_res = ld_out;
-    p.w_tiled = f.w_tiled ? 1 : 0;
-    p.gr_scratch = ws.P; p.gr_counter = ws.ctr + f.ctr_next; p.gr_kind = kind;
-    p.gr_out_bf16 = out_bf16; p.gr_stats_out = stats_out; p.gr_stats_in = stats_in; p.gr_fold_c = fold_c;
-    f.ctr_next += tiles;
-    return launch_gemm_tc(tw, tx, p, f.use_pdl, st);
+static int ln(const ArFast& f, const char* name, int rows, const float* x_in, const float* partial, int S, const float* bias,
+              const float* extra, float* x_out, const float* g, const float* be, h16* xn, cudaStream_t st) {
+    if (f.ln_cluster && f.cfg.embed_dim % 8 == 0 && f.cfg.embed_dim / 8 <= 3 * 192) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)rows * 2);
+        cfg.blockDim = dim3(192);
+        cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = f.use_pdl ? 1 : 0;
+        at[1].id = cudaLaunchAttributeClusterDimension;
+        at[1].val.clusterDim.x = 2;
+        at[1].val.clusterDim.y = 1;
+        at[1].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 2;
+        RQB_CUDA(cudaLaunchKernelEx(&cfg, ln_reduce2_kernel, x_in, partial, S, bias, extra, x_out, g, be, xn, rows, f.cfg.embed_dim, f.bf,
+                                    tr_slot(f, name)));
+        g_launches++;
+        return 0;
+    }
+    return launch_pdl(ln_reduce_kernel, dim3((unsigned)rows), dim3(384), (size_t)0, st, f.use_pdl, x_in, partial, S, bias, extra, x_out, g,
+                      be, xn, rows, f.cfg.embed_dim, f.bf, tr_slot(f, name));
 }
 
-// one transformer stack on the single new token of every batch row; x lives in `x` (fp32), residual additions are
-// deferred into the next ln_reduce.  On return the LAST block's fc2 partials (+ its bias) are still pending.
+static int attn(const ArFast& f, FastWs& ws, const float* bqkv, h16* kc, h16* vc, int Tmax, const int* t_ptr, int t_host,
+                cudaStream_t st) {
+    const rqb200_ar_config& c = f.cfg;
+    const size_t smem = (size_t)(4 * 64 + 4 * ((Tmax + 31) & ~31)) * sizeof(float);
+    // reading the position counter ahead of the dependency is only safe inside a captured graph (see the kernel)
+    return launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(f.B * c.n_head, 4)), dim3(128), smem, st, f.use_pdl,
+                      (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, t_ptr, t_host,
+                      (f.use_graph || t_ptr == nullptr) ? 1 : 0, f.bf, tr_slot(f, "attn"));
+}
+
+// one transformer stack on the single new token of every batch row; x lives in `x` (fp32); residual additions are deferred
+// into the next ln_reduce.
+// fin_g / fin_b (nullable): a LayerNorm applied to the stack's output rows -> ws.XN (the classifier's), fused with whatever
+// launch finishes x.
 static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& blocks, const std::vector<FastLayer>& maps,
-                      FastWs& ws, float* x, bool first_has_pending, const float* pending_bias, const float* pending_extra,
-                      const float* x_src, __nv_bfloat16* kc, __nv_bfloat16* vc, int Tmax, const int* t_ptr, int t_host,
-                      cudaStream_t st) {
+                      FastWs& ws, float* x, const float* pending_extra, const float* x_src, h16* kc, h16* vc, int Tmax,
+                      const int* t_ptr, int t_host, const float* fin_g, const float* fin_b, cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
     const int E = c.embed_dim, B = f.B;
     const int64_t per = (int64_t)B * c.n_head * Tmax * 64;
+    const float* nof = nullptr;
     for (size_t l = 0; l < blocks.size(); l++) {
         const rqb200_block_weights& bw = blocks[l];
-        if (f.gr) {
-            // ---- group-reduce form: x is final after proj / fc2; nothing is ever pending
-            const bool first = l == 0;
-            const bool need_copy = first && (x_src != x || pending_extra != nullptr);
-            const int nt = E / 128;
-            if (f.fold) {
-                if (first)
-                    RQB_TRY(launch_pdl(row_prep_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x_src,
-                                       (const float*)pending_extra, (float*)(need_copy ? x : nullptr), ws.XQ, ws.ST, B, E));
-                RQB_TRY(gemm(f, maps[l].qkv, f.tx_xq, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
-                             nullptr, 0, st));
-                RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
-                                   (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
-                                   c.n_head, Tmax, t_ptr, t_host, (const float2*)ws.ST, nt, (const float*)bw.cqkv));
-            } else {
-                RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)(first ? x_src : x),
-                                   (const float*)nullptr, 0, (const float*)nullptr, (const float*)(first ? pending_extra : nullptr),
-                                   (float*)(need_copy ? x : nullptr), (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
-                RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
-                             nullptr, 0, st));
-                RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
-                                   (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
-                                   c.n_head, Tmax, t_ptr, t_host, (const float2*)nullptr, 0, (const float*)nullptr));
-            }
-            RQB_TRY(gemm_gr(f, ws, maps[l].proj, f.tx_att, E, E, B, f.split_proj, 0, bw.bproj, x, E, x, f.fold ? ws.XQ : nullptr,
-                            f.fold ? ws.ST : nullptr, nullptr, nullptr, st));
-            if (!f.fold)
-                RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x,
-                                   (const float*)nullptr, 0, (const float*)nullptr, (const float*)nullptr, (float*)nullptr,
-                                   (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
-            RQB_TRY(gemm_gr(f, ws, maps[l].fc1, f.fold ? f.tx_xq : f.tx_xn, 4 * E, E, B, f.split_fc1, 1, bw.b1, ws.Hh, 4 * E, nullptr,
-                            nullptr, nullptr, f.fold ? ws.ST : nullptr, f.fold ? bw.c1 : nullptr, st));
-            RQB_TRY(gemm_gr(f, ws, maps[l].fc2, f.tx_h, E, 4 * E, B, f.split_fc2, 0, bw.b2, x, E, x, f.fold ? ws.XQ : nullptr,
-                            f.fold ? ws.ST : nullptr, nullptr, nullptr, st));
-            continue;
-        }
-        if (f.cluster) {
-            // ---- cluster split-K form: 6 kernels per block, no partial buffers except for qkv
-            const bool first = l == 0;
-            const bool need_copy = first && (x_src != x || pending_extra != nullptr);
-            RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)(first ? x_src : x),
-                               (const float*)nullptr, 0, (const float*)nullptr, (const float*)(first ? pending_extra : nullptr),
-                               (float*)(need_copy ? x : nullptr), (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
-            RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
-                         nullptr, 0, st));
-            RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
-                               (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
-                               c.n_head, Tmax, t_ptr, t_host, (const float2*)nullptr, 0, (const float*)nullptr));
-            RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.cl_proj, GT_F32, bw.bproj, 1.f, x, nullptr, x, E, nullptr, 0, st));
-            RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x,
-                               (const float*)nullptr, 0, (const float*)nullptr, (const float*)nullptr, (float*)nullptr,
-                               (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
-            RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.cl_fc1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr,
-                         0, st));
-            RQB_TRY(gemm(f, maps[l].fc2, f.tx_h, E, 4 * E, B, f.cl_fc2, GT_F32, bw.b2, 1.f, x, nullptr, x, E, nullptr, 0, st));
-            continue;
-        }
-        // LN1 (+ pending fc2 reduction of the previous block / previous stack)
-        const bool pend = l > 0 || first_has_pending;
-        const float* pb = l > 0 ? blocks[l - 1].b2 : pending_bias;
-        if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl,
-                           (const float*)(l == 0 ? x_src : x), (const float*)(pend ? ws.P : nullptr), pend ? f.split_fc2 : 0,
-                           (const float*)(pend ? pb : nullptr), (const float*)(l == 0 ? pending_extra : nullptr), x,
-                           (const float*)bw.ln1_w, (const float*)bw.ln1_b, ws.XN, B, E));
-        if (!(f.skip & 2)) RQB_TRY(gemm(f, maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
-                     nullptr, 0, st));
-        if (!(f.skip & 4)) RQB_TRY(launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(B * c.n_head, 4)), dim3(128), 0, st, f.use_pdl,
-                           (const float*)ws.P, f.split_qkv, (const float*)bw.bqkv, kc + per * l, vc + per * l, ws.ATT, B, E,
-                           c.n_head, Tmax, t_ptr, t_host, (const float2*)nullptr, 0, (const float*)nullptr));
-        if (!(f.skip & 8)) RQB_TRY(gemm(f, maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
-                     nullptr, 0, st));
-        if (!(f.skip & 1)) RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)x,
-                           (const float*)ws.P, f.split_proj, (const float*)bw.bproj, (const float*)nullptr, x,
-                           (const float*)bw.ln2_w, (const float*)bw.ln2_b, ws.XN, B, E));
+        const bool first = l == 0;
+        // LN1 (+ pending fc2 reduction of the previous block)
+        const bool pend = l > 0;
+        RQB_TRY(ln(f, "ln1", B, first ? x_src : x, pend ? ws.P : nof, pend ? f.split_fc2 : 0, pend ? blocks[l - 1].b2 : nof,
+                   first ? pending_extra : nof, x, bw.ln1_w, bw.ln1_b, ws.XN, st));
+        RQB_TRY(gemm(f, "qkv", maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr, 0,
+                     st));
+        RQB_TRY(attn(f, ws, bw.bqkv, kc + per * l, vc + per * l, Tmax, t_ptr, t_host, st));
+        RQB_TRY(gemm(f, "proj", maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr,
+                     0, st));
+        RQB_TRY(ln(f, "ln2", B, x, ws.P, f.split_proj, bw.bproj, nof, x, bw.ln2_w, bw.ln2_b, ws.XN, st));
         if (f.split_fc1 == 1) {
-            // fc1: either one CTA per 128-feature tile (48 CTAs at E=1536) or a 2-CTA cluster per tile with DSMEM reduction
-            if (!(f.skip & 16)) RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.fc1_cluster ? f.cl_fc1 : 1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr,
-                         nullptr, 0, nullptr, 0, st));
+            RQB_TRY(gemm(f, "fc1", maps[l].fc1, f.tx_xn, 4 * E, E, B, 1, GT_H16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr, 0, st,
+                         bw.w2, (int64_t)E * 4 * E * 2));
         } else {
-            RQB_TRY(gemm(f, maps[l].fc1, f.tx_xn, 4 * E, E, B, f.split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
-                         nullptr, 0, st));
-            RQB_TRY(launch_pdl(act_reduce_kernel, dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)B * 4 * E / 4, 256), 1184)), dim3(256), 0, st, f.use_pdl, (const float*)ws.P, f.split_fc1,
-                               (const float*)bw.b1, ws.Hh, B, 4 * E));
+            // fc2 only becomes resident when fc1's CTAs leave (shared memory) and act_reduce is short: its weights would stream
+            // from HBM on the critical path -- fc1's idle producer thread pulls them into L2 meanwhile
+            RQB_TRY(gemm(f, "fc1", maps[l].fc1, f.tx_xn, 4 * E, E, B, f.split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
+                         nullptr, 0, st, bw.w2, (int64_t)E * 4 * E * 2));
+            RQB_TRY(launch_pdl(act_reduce_kernel, dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)B * 4 * E / 4, 256), 1184)), dim3(256),
+                               (size_t)0, st, f.use_pdl, (const float*)ws.P, f.split_fc1, bw.b1, ws.Hh, B, 4 * E, f.bf,
+                               tr_slot(f, "act_reduce")));
         }
-        if (!(f.skip & 32)) RQB_TRY(gemm(f, maps[l].fc2, f.tx_h, E, 4 * E, B, f.split_fc2, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
-                     nullptr, 0, st));
+        RQB_TRY(gemm(f, "fc2", maps[l].fc2, f.tx_h, E, 4 * E, B, f.split_fc2, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr, 0,
+                     st));
     }
-    return 0;
-}
-
-// ---- persistent form: the same chains as fast_stack/record_*, expressed as phase tables for ar_mega_kernel
-static int build_programs(ArFast& f, FastWs& ws) {
-    const rqb200_ar_config& c = f.cfg;
-    const rqb200_ar_weights& w = f.w;
-    const int E = c.embed_dim, B = f.B, HW = c.H * c.W, Tb = c.cond_len + HW, D = c.D, V = c.vocab;
-    CUtensorMap mx_xn, mx_att, mx_h, mx_s;
-    RQB_TRY(make_tmap_2d(&mx_xn, ws.XN, 1, E, B, (uint64_t)E * 2, 64, 64));
-    RQB_TRY(make_tmap_2d(&mx_att, ws.ATT, 1, E, B, (uint64_t)E * 2, 64, 64));
-    RQB_TRY(make_tmap_2d(&mx_h, ws.Hh, 1, 4 * E, B, (uint64_t)E * 8, 64, 64));
-    RQB_TRY(make_tmap_2d(&mx_s, ws.S, 1, c.code_dim, B, (uint64_t)c.code_dim * 2, 64, 64));
-    std::vector<MPhase> all;
-    auto ln = [&](const float* x_in, bool pend, int S, const float* bias, const float* extra, float* x_out, const float* g,
-                  const float* be, __nv_bfloat16* xn) {
-        MPhase p = {};
-        p.type = MP_LN; p.x_in = x_in; p.partial = pend ? ws.P : nullptr; p.S = pend ? S : 0; p.bias = pend ? bias : nullptr;
-        p.extra = extra; p.x_out = x_out; p.g = g; p.be = be; p.xn = xn;
-        all.push_back(p);
-    };
-    auto gm = [&](const CUtensorMap& tw, const CUtensorMap& tx, int N_out, int K, int splits, int mode, const float* bias,
-                  float bias_scale, void* out, const float* res, int64_t ld_res, const int* res_row_ptr, int64_t res_row_stride) {
-        MPhase p = {};
-        p.type = MP_GEMM; p.tmW = tw; p.tmX = tx; p.N_out = N_out; p.K = K; p.splits = splits; p.mode = mode; p.gbias = bias;
-        p.w_tiled = f.w_tiled ? 1 : 0;
-        p.bias_scale = bias_scale; p.out = out; p.gpartial = ws.P; p.res = res; p.ld_res = ld_res; p.res_row_ptr = res_row_ptr;
-        p.res_row_stride = res_row_stride;
-        all.push_back(p);
-    };
-    auto stack = [&](const std::vector<rqb200_block_weights>& blocks, const std::vector<FastLayer>& maps, float* x, bool first_pending,
-                     const float* pending_bias, const float* pending_extra, const float* x_src, __nv_bfloat16* kc,
-                     __nv_bfloat16* vc, int Tmax, const int* t_ptr, int t_host) {
-        const int64_t per = (int64_t)B * c.n_head * Tmax * 64;
-        for (size_t l = 0; l < blocks.size(); l++) {
-            const rqb200_block_weights& bw = blocks[l];
-            const bool pend = l > 0 || first_pending;
-            ln(l == 0 ? x_src : x, pend, f.split_fc2, l > 0 ? blocks[l - 1].b2 : pending_bias, l == 0 ? pending_extra : nullptr, x,
-               bw.ln1_w, bw.ln1_b, ws.XN);
-            gm(maps[l].qkv, mx_xn, 3 * E, E, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, nullptr, 0, nullptr, 0);
-            MPhase a = {};
-            a.type = MP_ATTN; a.apart = ws.P; a.aS = f.split_qkv; a.bqkv = bw.bqkv; a.kc = kc + per * l; a.vc = vc + per * l;
-            a.att = ws.ATT; a.Tmax = Tmax; a.t_ptr = t_ptr; a.t_host = t_host;
-            all.push_back(a);
-            gm(maps[l].proj, mx_att, E, E, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, nullptr, 0, nullptr, 0);
-            ln(x, true, f.split_proj, bw.bproj, nullptr, x, bw.ln2_w, bw.ln2_b, ws.XN);
-            if (f.mega_split_fc1 <= 1) {
-                gm(maps[l].fc1, mx_xn, 4 * E, E, 1, GT_BF16_GELU, bw.b1, 1.f, ws.Hh, nullptr, 0, nullptr, 0);
-            } else {
-                gm(maps[l].fc1, mx_xn, 4 * E, E, f.mega_split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, nullptr, 0, nullptr, 0);
-                MPhase a2 = {};
-                a2.type = MP_ACT; a2.N_out = 4 * E; a2.splits = f.mega_split_fc1; a2.gbias = bw.b1; a2.gpartial = ws.P; a2.out = ws.Hh;
-                all.push_back(a2);
-            }
-            gm(maps[l].fc2, mx_h, E, 4 * E, f.split_fc2, GT_PARTIAL, nullptr, 1.f, nullptr, nullptr, 0, nullptr, 0);
-        }
-    };
-    auto cs = [&](int mode) {
-        MPhase p = {};
-        p.type = MP_CODESUM; p.cs_mode = mode; p.cs_out = ws.S;
-        all.push_back(p);
-    };
-    std::vector<std::pair<size_t, size_t>> spans;      // [begin, end) per program: cond, code, head 0..D-1
-    size_t b0 = all.size();
-    stack(f.body, f.lbody, ws.XB, false, nullptr, nullptr, ws.XB, ws.kc_body, ws.vc_body, Tb, &ws.state->s, 0);
-    spans.push_back({b0, all.size()});
-    b0 = all.size();
-    cs(0);
-    gm(f.tm_win, mx_s, E, c.code_dim, 1, GT_F32, w.b_in, (float)D, ws.XB, w.pos_emb_hw - E, 0, &ws.state->idx, E);
-    stack(f.body, f.lbody, ws.XB, false, nullptr, nullptr, ws.XB, ws.kc_body, ws.vc_body, Tb, &ws.state->s, 0);
-    spans.push_back({b0, all.size()});
-    for (int d = 0; d < D; d++) {
-        b0 = all.size();
-        if (d == 0) {
-            stack(f.head, f.lhead, ws.XH, true, f.body.back().b2, w.pos_emb_d, ws.XB, ws.kc_head, ws.vc_head, D, nullptr, 0);
-        } else {
-            cs(d);
-            gm(f.tm_whead, mx_s, E, c.code_dim, 1, GT_F32, w.b_head, 1.f, ws.XH, w.pos_emb_d + (int64_t)d * E, 0, nullptr, 0);
-            stack(f.head, f.lhead, ws.XH, false, nullptr, nullptr, ws.XH, ws.kc_head, ws.vc_head, D, nullptr, d);
-        }
-        ln(ws.XH, true, f.split_fc2, f.head.back().b2, nullptr, nullptr, w.cls_ln_w, w.cls_ln_b, ws.XN);
-        gm(f.tm_cls, mx_xn, V, E, 1, GT_F32, w.b_cls, 1.f, ws.LOGITS, nullptr, 0, nullptr, 0);
-        spans.push_back({b0, all.size()});
-    }
-    // one synchronous upload per (workspace, batch) binding
-    RQB_CUDA(cudaMemcpy(ws.tables, all.data(), all.size() * sizeof(MPhase), cudaMemcpyHostToDevice));
-    RQB_CUDA(cudaMemset(ws.bar, 0, 64 * sizeof(unsigned)));
-    auto mk = [&](std::pair<size_t, size_t> sp) {
-        MegaParams P = {};
-        P.phases = ws.tables + sp.first; P.n_phases = (int)(sp.second - sp.first);
-        P.B = B; P.E = E; P.nh = c.n_head; P.bar = ws.bar; P.stt = ws.state;
-        P.codebook = w.codebook; P.HW = HW; P.D = D; P.Kc = c.codebook_size; P.C = c.code_dim;
-        P.trace = (getenv("RQB200_MEGA_TRACE") && P.n_phases < 2000) ? ws.trace : nullptr;
-        return P;
-    };
-    f.prog_cond = mk(spans[0]);
-    f.prog_code = mk(spans[1]);
-    for (int d = 0; d < D; d++) f.prog_head[d] = mk(spans[2 + d]);
+    // fold the last block's pending fc2 reduction into x (x is final on return) -- and the caller's LayerNorm, if any
+    RQB_TRY(ln(f, "finalize", B, x, ws.P, f.split_fc2, blocks.back().b2, nof, x, fin_g, fin_b, fin_g ? ws.XN : nullptr, st));
     return 0;
 }
 
@@ -670,73 +704,56 @@ static int record_body(ArFast& f, FastWs& ws, bool cond_token, cudaStream_t st) 
     const rqb200_ar_config& c = f.cfg;
     const rqb200_ar_weights& w = f.w;
     const int E = c.embed_dim, B = f.B, HW = c.H * c.W, Tb = c.cond_len + HW;
-    if (f.use_mega) {
-        if (cond_token)
-            RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B), dim3(256), 0, st, false, (const StepState*)ws.state, w.cond_emb,
-                               w.pos_emb_cond, c.cond_len, c.vocab_cond, E, ws.XB));
-        RQB_TRY(launch_ar_mega(cond_token ? f.prog_cond : f.prog_code, f.n_sm, st));
-        RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, false, ws.state, 1, 0, 0));
-        return 0;
-    }
-    f.ctr_next = 0;
     if (cond_token) {
-        RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B), dim3(256), 0, st, f.use_pdl, (const StepState*)ws.state, w.cond_emb,
+        RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B, 1), dim3(256), (size_t)0, st, f.use_pdl, (const StepState*)ws.state, w.cond_emb,
                            w.pos_emb_cond, c.cond_len, c.vocab_cond, E, ws.XB));
     } else {
-        RQB_TRY(launch_pdl(code_sum_kernel, dim3(B), dim3(64), 0, st, f.use_pdl, (const StepState*)ws.state, w.codebook, HW, c.D,
-                           c.codebook_size, c.code_dim, 0, ws.S));
+        RQB_TRY(launch_pdl(code_sum_kernel, dim3(B, 1), dim3(64), (size_t)0, st, f.use_pdl, (const StepState*)ws.state, w.codebook, HW,
+                           c.D, c.codebook_size, c.code_dim, 0, 0, ws.S, f.bf));
         // x = W_in (sum_d e_d) + D b_in + pos_emb_hw[idx-1]       (bias counted D times, transformers.py:220,225)
-        RQB_TRY(gemm(f, f.tm_win, f.tx_s, E, c.code_dim, B, 1, GT_F32, w.b_in, (float)c.D, ws.XB, nullptr,
+        RQB_TRY(gemm(f, "w_in", f.tm_win, f.tx_s, E, c.code_dim, B, 1, GT_F32, w.b_in, (float)c.D, ws.XB, nullptr,
                      w.pos_emb_hw - E /* row idx-1 */, 0, &ws.state->idx, E, st));
     }
-    RQB_TRY(fast_stack(f, f.body, f.lbody, ws, ws.XB, false, nullptr, nullptr, ws.XB, ws.kc_body, ws.vc_body, Tb, &ws.state->s,
-                       0, st));
-    if (f.gr) RQB_TRY(launch_pdl(ctr_zero_kernel, dim3(1), dim3(256), 0, st, f.use_pdl, ws.ctr, f.ctr_next));
-    RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, f.use_pdl, ws.state, 1, 0, 0));
+    RQB_TRY(fast_stack(f, f.body, f.lbody, ws, ws.XB, nullptr, ws.XB, ws.kc_body, ws.vc_body, Tb, &ws.state->s, 0, nullptr, nullptr, st));
+    RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), (size_t)0, st, f.use_pdl, ws.state, 1, 0, 0));
     return 0;
 }
 
-static int record_head(ArFast& f, FastWs& ws, cudaStream_t st) {
+static int record_head(ArFast& f, FastWs& ws, bool with_logits, cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
     const rqb200_ar_weights& w = f.w;
     const int E = c.embed_dim, B = f.B, HW = c.H * c.W, D = c.D, V = c.vocab;
-    if (f.use_mega) {
-        for (int d = 0; d < D; d++) {
-            RQB_TRY(launch_ar_mega(f.prog_head[d], f.n_sm, st));
-            RQB_TRY(launch_pdl(logits_copy_kernel, dim3(64), dim3(256), 0, st, false, (const StepState*)ws.state,
-                               (const float*)ws.LOGITS, d, (int64_t)B * V));
-            RQB_TRY(launch_sample_dyn(ws.LOGITS, ws.state, d, B, V, HW, D, st, false));
-        }
-        RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, false, ws.state, 0, 1, D));
-        return 0;
-    }
-    f.ctr_next = 0;
     for (int d = 0; d < D; d++) {
         if (d == 0) {
-            // spatial ctx = body x + pending fc2 of the last body block ; token = ctx + pos_emb_d[0]  (transformers.py:259-270)
-            RQB_TRY(fast_stack(f, f.head, f.lhead, ws, ws.XH, true, f.body.back().b2, w.pos_emb_d, ws.XB, ws.kc_head, ws.vc_head,
-                               D, nullptr, 0, st));
+            // token = spatial ctx (body output) + pos_emb_d[0]                                   (transformers.py:259-270)
+            RQB_TRY(fast_stack(f, f.head, f.lhead, ws, ws.XH, w.pos_emb_d, ws.XB, ws.kc_head, ws.vc_head, D, nullptr, 0, w.cls_ln_w,
+                               w.cls_ln_b, st));
         } else {
-            RQB_TRY(launch_pdl(code_sum_kernel, dim3(B), dim3(64), 0, st, f.use_pdl, (const StepState*)ws.state, w.codebook, HW, D,
-                               c.codebook_size, c.code_dim, d, ws.S));
-            RQB_TRY(gemm(f, f.tm_whead, f.tx_s, E, c.code_dim, B, 1, GT_F32, w.b_head, 1.f, ws.XH, nullptr,
+            RQB_TRY(launch_pdl(code_sum_kernel, dim3(B, 1), dim3(64), (size_t)0, st, f.use_pdl, (const StepState*)ws.state, w.codebook,
+                               HW, D, c.codebook_size, c.code_dim, d, 0, ws.S, f.bf));
+            RQB_TRY(gemm(f, "w_head", f.tm_whead, f.tx_s, E, c.code_dim, B, 1, GT_F32, w.b_head, 1.f, ws.XH, nullptr,
                          w.pos_emb_d + (int64_t)d * E, 0, nullptr, 0, st));
-            RQB_TRY(fast_stack(f, f.head, f.lhead, ws, ws.XH, false, nullptr, nullptr, ws.XH, ws.kc_head, ws.vc_head, D, nullptr, d,
-                               st));
+            RQB_TRY(fast_stack(f, f.head, f.lhead, ws, ws.XH, nullptr, ws.XH, ws.kc_head, ws.vc_head, D, nullptr, d, w.cls_ln_w,
+                               w.cls_ln_b, st));
         }
-        // classifier: LN(x + pending fc2) -> logits                                              (transformers.py:278-285)
-        RQB_TRY(launch_pdl(ln_reduce_kernel, dim3(B), dim3(384), (size_t)0, st, f.use_pdl, (const float*)ws.XH,
-                           (const float*)((f.cluster || f.gr) ? nullptr : ws.P), (f.cluster || f.gr) ? 0 : f.split_fc2,
-                           (const float*)((f.cluster || f.gr) ? nullptr : f.head.back().b2), (const float*)nullptr, (float*)nullptr, w.cls_ln_w,
-                           w.cls_ln_b, ws.XN, B, E));
-        RQB_TRY(gemm(f, f.tm_cls, f.tx_xn, V, E, B, 1, GT_F32, w.b_cls, 1.f, ws.LOGITS, nullptr, nullptr, 0, nullptr, 0, st));
-        RQB_TRY(launch_pdl(logits_copy_kernel, dim3(64), dim3(256), 0, st, f.use_pdl, (const StepState*)ws.state,
-                           (const float*)ws.LOGITS, d, (int64_t)B * V));
+        // classifier: LN(x) (fused into the stack's last launch) -> logits                       (transformers.py:278-285)
+        RQB_TRY(gemm(f, "cls", f.tm_cls, f.tx_xn, V, E, B, 1, GT_F32, w.b_cls, 1.f, ws.LOGITS, nullptr, nullptr, 0, nullptr, 0, st));
+        if (with_logits)
+            RQB_TRY(launch_pdl(logits_copy_kernel, dim3(64), dim3(256), (size_t)0, st, f.use_pdl, (const StepState*)ws.state,
+                               (const float*)ws.LOGITS, d, (int64_t)B * V));
         RQB_TRY(launch_sample_dyn(ws.LOGITS, ws.state, d, B, V, HW, D, st, f.use_pdl));
     }
-    if (f.gr) RQB_TRY(launch_pdl(ctr_zero_kernel, dim3(1), dim3(256), 0, st, f.use_pdl, ws.ctr, f.ctr_next));
-    RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, f.use_pdl, ws.state, 0, 1, D));
+    RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), (size_t)0, st, f.use_pdl, ws.state, 0, 1, D));
     return 0;
+}
+
+static int record(ArFast& f, FastWs& ws, int which, cudaStream_t st) {
+    f.tr_base = ws.trace;
+    f.tr_next = f.tr_graph_base[which];
+    int rc = which == G_COND ? record_body(f, ws, true, st) : which == G_CODE ? record_body(f, ws, false, st)
+                                                                                : record_head(f, ws, which == G_HEAD_LOGITS, st);
+    // trace slots: every graph owns a quarter of the buffer
+    return rc;
 }
 
 static int capture(ArFast& f, FastWs& ws, int which, cudaGraphExec_t* out) {
@@ -745,7 +762,7 @@ static int capture(ArFast& f, FastWs& ws, int which, cudaGraphExec_t* out) {
     cudaStream_t st = f.cap_stream;
     RQB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     const int64_t before = g_launches;
-    int rc = which == 0 ? record_body(f, ws, true, st) : which == 1 ? record_body(f, ws, false, st) : record_head(f, ws, st);
+    int rc = record(f, ws, which, st);
     f.n_nodes[which] = g_launches - before;
     g_launches = before;                   // recording is not launching
     cudaError_t e = cudaStreamEndCapture(st, &g);
@@ -758,10 +775,10 @@ static int capture(ArFast& f, FastWs& ws, int which, cudaGraphExec_t* out) {
 }
 
 static void drop_graphs(ArFast& f) {
-    if (f.g_cond) cudaGraphExecDestroy(f.g_cond);
-    if (f.g_code) cudaGraphExecDestroy(f.g_code);
-    if (f.g_head) cudaGraphExecDestroy(f.g_head);
-    f.g_cond = f.g_code = f.g_head = nullptr;
+    for (int i = 0; i < G_COUNT; i++) {
+        if (f.graphs[i]) cudaGraphExecDestroy(f.graphs[i]);
+        f.graphs[i] = nullptr;
+    }
 }
 
 ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, const rqb200_block_weights* body_p,
@@ -774,64 +791,42 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     }
     ArFast* f = new ArFast();
     f->cfg = cfg; f->w = w; f->body = body; f->head = head;
-    f->w_tiled = (cfg.mode & 0x100) != 0;              // bit 8 of `mode`: fast-tier weights are tile-major
-    const char* e;
-    if ((e = getenv("RQB200_NO_GRAPH")) && e[0] == '1') f->use_graph = false;
-    if ((e = getenv("RQB200_NO_PDL")) && e[0] == '1') f->use_pdl = false;
-    if ((e = getenv("RQB200_MEGA")) && e[0] == '1') f->want_mega = true;
-    if ((e = getenv("RQB200_CLUSTER")) && e[0] == '1') f->cluster = true;
-    if ((e = getenv("RQB200_SKIP"))) f->skip = atoi(e);
-    if ((e = getenv("RQB200_FC1_CLUSTER"))) { f->cl_fc1 = atoi(e); f->fc1_cluster = f->cl_fc1 > 1; }
-    f->cl_proj = std::min(8, E / 64);
-    f->cl_fc2 = std::min(8, 4 * E / 64);
-    f->cl_fc1 = std::min(f->cl_fc1, E / 64);
-    if ((e = getenv("RQB200_MEGA_SPLIT_FC1"))) f->mega_split_fc1 = atoi(e);
-    f->mega_split_fc1 = pick_split(4 * E / 128, E / 64, f->mega_split_fc1);
+    f->bf = cfg.weight_dtype == RQB200_BF16 ? 1 : 0;
+    f->use_graph = !(cfg.flags & RQB200_AR_NO_GRAPH);
+    f->use_pdl = !(cfg.flags & RQB200_AR_NO_PDL);
+    f->trace = (cfg.flags & RQB200_AR_TRACE) != 0;
+    f->l2pf = (cfg.flags & RQB200_AR_L2_PREFETCH) != 0;
+    f->deep = !(cfg.flags & RQB200_AR_SHALLOW_RING);
+    f->batched_prefill = !(cfg.flags & RQB200_AR_SEQUENTIAL_PREFILL);
+    f->next_pf = !(cfg.flags & RQB200_AR_NO_NEXT_PREFETCH);
+    f->ln_cluster = (cfg.flags & RQB200_AR_LN_CLUSTER) != 0;
     {
         int dev = 0, n = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) f->n_sm = n;
     }
     const int nkbE = E / 64;
-    f->split_qkv = pick_split(3 * E / 128, nkbE, getenv("RQB200_SPLIT_QKV") ? atoi(getenv("RQB200_SPLIT_QKV")) : 0);
-    f->split_proj = pick_split(E / 128, nkbE, getenv("RQB200_SPLIT_PROJ") ? atoi(getenv("RQB200_SPLIT_PROJ")) : 0);
-    f->split_fc1 = pick_split(4 * E / 128, nkbE, getenv("RQB200_SPLIT_FC1") ? atoi(getenv("RQB200_SPLIT_FC1")) : 0);
-    f->split_fc2 = pick_split(E / 128, 4 * nkbE, getenv("RQB200_SPLIT_FC2") ? atoi(getenv("RQB200_SPLIT_FC2")) : 0);
-    {
-        bool all_fold = true, any_fold = false;
-        for (const auto& b : body) { all_fold &= (b.cqkv && b.c1); any_fold |= (b.cqkv || b.c1); }
-        for (const auto& b : head) { all_fold &= (b.cqkv && b.c1); any_fold |= (b.cqkv || b.c1); }
-        if ((e = getenv("RQB200_GR")) && e[0] == '1') f->gr = true;
-        // every CTA of a GT_GR grid spins for its tile's peers: the whole grid has to be resident (one CTA per SM)
-        const int g_max = std::max(std::max(E / 128 * f->split_proj, 4 * E / 128 * f->split_fc1), E / 128 * f->split_fc2);
-        if (f->gr && (g_max > f->n_sm || f->cluster || f->want_mega || E % 128 != 0)) {
-            fprintf(stderr, "rqb200: RQB200_GR ignored (a GEMM grid of %d CTAs would not be co-resident on %d SMs, or another chain form is selected)\n",
-                    g_max, f->n_sm);
-            f->gr = false;
-        }
-        f->fold = f->gr && all_fold;
-        if (any_fold && !f->fold) {
-            set_error("ar fast tier: LayerNorm-folded weights (rqb200_block_weights.cqkv / .c1) need the RQB200_GR=1 chain and must be given for every block");
-            delete f;
-            return nullptr;
-        }
-    }
+    f->split_qkv = pick_split(3 * E / 128, nkbE, cfg.split_qkv, f->n_sm);
+    f->split_proj = pick_split(E / 128, nkbE, cfg.split_proj, f->n_sm);
+    f->split_fc1 = pick_split(4 * E / 128, nkbE, cfg.split_fc1, f->n_sm);
+    f->split_fc2 = pick_split(E / 128, 4 * nkbE, cfg.split_fc2, f->n_sm);
     auto mk = [&](const std::vector<rqb200_block_weights>& bl, std::vector<FastLayer>& out) -> int {
         out.resize(bl.size());
         for (size_t l = 0; l < bl.size(); l++) {
-            RQB_TRY(make_tmap_weight(&out[l].qkv, bl[l].wqkv, 3 * E, E, f->w_tiled));
-            RQB_TRY(make_tmap_weight(&out[l].proj, bl[l].wproj, E, E, f->w_tiled));
-            RQB_TRY(make_tmap_weight(&out[l].fc1, bl[l].w1, 4 * E, E, f->w_tiled));
-            RQB_TRY(make_tmap_weight(&out[l].fc2, bl[l].w2, E, 4 * E, f->w_tiled));
+            RQB_TRY(make_tmap_weight(&out[l].qkv, bl[l].wqkv, 3 * E, E));
+            RQB_TRY(make_tmap_weight(&out[l].proj, bl[l].wproj, E, E));
+            RQB_TRY(make_tmap_weight(&out[l].fc1, bl[l].w1, 4 * E, E));
+            RQB_TRY(make_tmap_weight(&out[l].fc2, bl[l].w2, E, 4 * E));
         }
         return 0;
     };
     int rc = mk(body, f->lbody);
     if (!rc) rc = mk(head, f->lhead);
-    if (!rc) rc = make_tmap_weight(&f->tm_win, w.w_in, E, cfg.code_dim, f->w_tiled);
-    if (!rc) rc = make_tmap_weight(&f->tm_whead, w.w_head, E, cfg.code_dim, f->w_tiled);
-    if (!rc) rc = make_tmap_weight(&f->tm_cls, w.w_cls, cfg.vocab, E, f->w_tiled);
+    if (!rc) rc = make_tmap_weight(&f->tm_win, w.w_in, E, cfg.code_dim);
+    if (!rc) rc = make_tmap_weight(&f->tm_whead, w.w_head, E, cfg.code_dim);
+    if (!rc) rc = make_tmap_weight(&f->tm_cls, w.w_cls, cfg.vocab, E);
     if (rc) { delete f; return nullptr; }
+    for (int i = 0; i <= G_COUNT; i++) f->tr_graph_base[i] = i * (TR_CAP / G_COUNT);
     return f;
 }
 
@@ -844,21 +839,93 @@ void ar_fast_destroy(ArFast* f) {
 
 size_t ar_fast_workspace_bytes(const ArFast* f, int B) { return fast_layout(*f, B, nullptr, 0, nullptr); }
 
-int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B, int start_h, int start_w, float temperature,
-                   const int32_t* top_k, const float* top_p, const float* noise, int64_t noise_stride, float* logits_out,
-                   const int64_t* force, int64_t* out, void* wsp, size_t ws_bytes, cudaStream_t st) {
+// ---- batched prefill: body tokens [s0, s0 + T) of every batch row in one pass (rows token-major: row = t * B + b).
+// Token s < cond_len is a cond token; token s >= cond_len carries the codes of position s - cond_len.  Requires s0 == 0
+// (the causal attention kernel sees the whole prefix) and T <= PA_MAXT.  Leaves ws.XB = the last token's output rows, the KV
+// cache rows [0, T) written, state.s = T.
+static int prefill_batched(ArFast& f, FastWs& ws, int T, cudaStream_t st) {
+    const rqb200_ar_config& c = f.cfg;
+    const rqb200_ar_weights& w = f.w;
+    const int E = c.embed_dim, B = f.B, HW = c.H * c.W, cl = c.cond_len, Tb = cl + HW;
+    const int64_t M = (int64_t)B * T;
+    if (M > ws.Mmax || T > PA_MAXT) return fail(RQB200_EINVAL, "ar fast tier: prefix too long for the batched prefill");
+    const bool pdl = false;              // large launches: plain stream order
+    CUtensorMap tx_xn, tx_att, tx_h, tx_s;
+    const int bn = gemm_tc_bn((int)std::min<int64_t>(M, 256));
+    RQB_TRY(make_tmap_2d(&tx_xn, ws.PXN, 1, E, M, (uint64_t)E * 2, 64, bn));
+    RQB_TRY(make_tmap_2d(&tx_att, ws.PATT, 1, E, M, (uint64_t)E * 2, 64, bn));
+    RQB_TRY(make_tmap_2d(&tx_h, ws.PH, 1, 4 * E, M, (uint64_t)E * 8, 64, bn));
+    const bool save_pdl = f.use_pdl, save_tr = f.trace;
+    f.use_pdl = pdl;
+    f.trace = false;
+    int rc = [&]() -> int {
+        // tokens
+        RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B, std::min(T, cl)), dim3(256), (size_t)0, st, pdl, (const StepState*)ws.state, w.cond_emb,
+                           w.pos_emb_cond, cl, c.vocab_cond, E, ws.PX));
+        const int n_code = T - cl;       // code tokens of positions 0 .. n_code-1
+        if (n_code > 0) {
+            const int64_t Mc = (int64_t)B * n_code;
+            RQB_TRY(make_tmap_2d(&tx_s, ws.PS, 1, c.code_dim, Mc, (uint64_t)c.code_dim * 2, 64, gemm_tc_bn((int)std::min<int64_t>(Mc, 256))));
+            RQB_TRY(launch_pdl(code_sum_kernel, dim3(B, n_code), dim3(64), (size_t)0, st, pdl, (const StepState*)ws.state, w.codebook, HW,
+                               c.D, c.codebook_size, c.code_dim, -1, 0, ws.PS, f.bf));
+            GemmTcParams p = gemm_base(f, E, c.code_dim, (int)Mc, 1, GT_F32);
+            p.bias = w.b_in; p.bias_scale = (float)c.D; p.out = ws.PX + (int64_t)cl * B * E;
+            p.residual = w.pos_emb_hw; p.ld_res = E; p.res_div = B;          // row (j, b) gets pos_emb_hw[j]
+            RQB_TRY(launch_gemm_tc(f.tm_win, tx_s, p, pdl, st));
+        }
+        const float* nof = nullptr;
+        for (size_t l = 0; l < f.body.size(); l++) {
+            const rqb200_block_weights& bw = f.body[l];
+            const int64_t per = (int64_t)B * c.n_head * Tb * 64;
+            RQB_TRY(ln(f, "", (int)M, ws.PX, nof, 0, nof, nof, nullptr, bw.ln1_w, bw.ln1_b, ws.PXN, st));
+            {
+                GemmTcParams p = gemm_base(f, 3 * E, E, (int)M, 1, GT_H16);
+                p.bias = bw.bqkv; p.out = ws.PQKV;
+                RQB_TRY(launch_gemm_tc(f.lbody[l].qkv, tx_xn, p, pdl, st));
+            }
+            RQB_TRY(launch_pdl(prefill_attn_kernel, dim3((unsigned)(B * c.n_head)), dim3(128), (size_t)0, st, pdl, (const h16*)ws.PQKV,
+                               ws.kc_body + per * l, ws.vc_body + per * l, ws.PATT, B, T, E, c.n_head, Tb, f.bf));
+            {
+                GemmTcParams p = gemm_base(f, E, E, (int)M, 1, GT_F32);
+                p.bias = bw.bproj; p.out = ws.PX; p.residual = ws.PX; p.ld_res = E;
+                RQB_TRY(launch_gemm_tc(f.lbody[l].proj, tx_att, p, pdl, st));
+            }
+            RQB_TRY(ln(f, "", (int)M, ws.PX, nof, 0, nof, nof, nullptr, bw.ln2_w, bw.ln2_b, ws.PXN, st));
+            {
+                GemmTcParams p = gemm_base(f, 4 * E, E, (int)M, 1, GT_H16_GELU);
+                p.bias = bw.b1; p.out = ws.PH;
+                RQB_TRY(launch_gemm_tc(f.lbody[l].fc1, tx_xn, p, pdl, st));
+            }
+            {
+                GemmTcParams p = gemm_base(f, E, 4 * E, (int)M, 1, GT_F32);
+                p.bias = bw.b2; p.out = ws.PX; p.residual = ws.PX; p.ld_res = E;
+                RQB_TRY(launch_gemm_tc(f.lbody[l].fc2, tx_h, p, pdl, st));
+            }
+        }
+        RQB_CUDA(cudaMemcpyAsync(ws.XB, ws.PX + (int64_t)(T - 1) * B * E, (size_t)B * E * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), (size_t)0, st, false, ws.state, T, 0, 0));
+        return 0;
+    }();
+    f.use_pdl = save_pdl;
+    f.trace = save_tr;
+    return rc;
+}
+
+int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B, int idx_begin, int idx_end, int resume,
+                   float temperature, const int32_t* top_k, const float* top_p, const float* noise, int64_t noise_stride,
+                   float* logits_out, const int64_t* force, int64_t* out, void* wsp, size_t ws_bytes, cudaStream_t st) {
     const rqb200_ar_config& c = f->cfg;
     const int E = c.embed_dim, D = c.D, HW = c.H * c.W, cl = c.cond_len;
     if (B < 1 || B > 256) return fail(RQB200_EINVAL, "ar fast tier: batch must be in [1,256] per call");
-    if (start_h < 0 || start_w < 0 || start_w >= c.W || start_h > c.H) return fail(RQB200_EINVAL, "ar_sample: bad start_loc");
+    if (idx_begin < 0 || idx_end > HW || idx_begin > idx_end) return fail(RQB200_EINVAL, "ar_sample: bad position span");
     FastWs ws;
     size_t need = fast_layout(*f, B, wsp, ws_bytes, &ws);
     if (need > ws_bytes) return fail(RQB200_EWORKSPACE, "ar_sample: workspace too small");
-    if (out != partial)
+    if (!resume && out != partial)
         RQB_CUDA(cudaMemcpyAsync(out, partial, (size_t)B * HW * D * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-    const int idx0 = start_h * c.W + start_w;
-    if (idx0 >= HW) return 0;
+    if (idx_begin >= idx_end) return 0;
     if (f->ws_base != wsp || f->B != B) {        // (re)bind activation tensor maps + graphs to this workspace
+        if (resume) return fail(RQB200_ESTATE, "ar_sample: resume on a workspace / batch the engine is not bound to");
         drop_graphs(*f);
         f->ws_base = wsp;
         f->B = B;
@@ -867,60 +934,61 @@ int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B
         RQB_TRY(make_tmap_2d(&f->tx_att, ws.ATT, 1, E, B, (uint64_t)E * 2, 64, bn));
         RQB_TRY(make_tmap_2d(&f->tx_h, ws.Hh, 1, 4 * E, B, (uint64_t)E * 8, 64, bn));
         RQB_TRY(make_tmap_2d(&f->tx_s, ws.S, 1, c.code_dim, B, (uint64_t)c.code_dim * 2, 64, bn));
-        RQB_TRY(make_tmap_2d(&f->tx_xq, ws.XQ, 1, E, B, (uint64_t)E * 2, 64, bn));
-        f->use_mega = f->want_mega && B <= 64 && E <= 224 * 4 * 3 && mega_smem_bytes(E) <= 227 * 1024;
-        if (f->use_mega) RQB_TRY(build_programs(*f, ws));
     }
     StepState h = {};
     h.s = 0; h.idx = 0; h.step = 0;
     h.cond = cond; h.codes = out; h.force = force; h.noise = noise; h.logits_out = logits_out; h.noise_stride = noise_stride;
     h.temperature = temperature;
     for (int d = 0; d < D; d++) { h.top_k[d] = top_k[d]; h.top_p[d] = top_p[d]; }
-    RQB_TRY(launch_pdl(init_state_kernel, dim3(1), dim3(32), 0, st, false, ws.state, h));
-    if (f->gr) RQB_CUDA(cudaMemsetAsync(ws.ctr, 0, (size_t)ws.ctr_cap * sizeof(unsigned), st));
-    auto run = [&](int which, cudaGraphExec_t* g) -> int {
-        if (!f->use_graph) return which == 0 ? record_body(*f, ws, true, st) : which == 1 ? record_body(*f, ws, false, st)
-                                                                                        : record_head(*f, ws, st);
-        if (!*g) RQB_TRY(capture(*f, ws, which, g));
-        RQB_CUDA(cudaGraphLaunch(*g, st));
+    RQB_TRY(launch_pdl(init_state_kernel, dim3(1), dim3(32), (size_t)0, st, false, ws.state, h, resume ? 1 : 0));
+    if (f->trace && !resume) RQB_CUDA(cudaMemsetAsync(ws.trace, 0, (size_t)4 * TR_CAP * sizeof(long long), st));
+    auto run = [&](int which) -> int {
+        if (!f->use_graph) return record(*f, ws, which, st);
+        if (!f->graphs[which]) RQB_TRY(capture(*f, ws, which, &f->graphs[which]));
+        RQB_CUDA(cudaGraphLaunch(f->graphs[which], st));
         g_launches += f->n_nodes[which];     // kernels executed by this replay
         return 0;
     };
-    // prefill: cond tokens, then (resume) the code tokens of positions < idx0, one cached step each -- causal, so
-    // identical to the reference's batched prefill (transformers.py:237-239)
-    for (int s = 0; s < cl; s++) RQB_TRY(run(0, &f->g_cond));
-    // state.idx must equal (position whose codes feed the body) + 1 while replaying the code-token graph
-    for (int j = 1; j <= idx0; j++) {
-        RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, st, false, ws.state, 0, 1, 0));
-        RQB_TRY(run(1, &f->g_code));
-    }
-    for (int idx = idx0; idx < HW; idx++) {
-        if (idx > idx0) RQB_TRY(run(1, &f->g_code));       // body step on the token of position idx-1 (state.idx == idx)
-        RQB_TRY(run(2, &f->g_head));                       // D head steps + sampling; advances idx, step
-    }
-    if (f->use_mega && getenv("RQB200_MEGA_TRACE")) {      // diagnostics: per-phase time of the LAST launch that wrote the trace
-        cudaStreamSynchronize(st);
-        std::vector<long long> tr(4096);
-        std::vector<MPhase> ph(f->prog_head[D - 1].n_phases);
-        cudaMemcpy(tr.data(), ws.trace, 4096 * sizeof(long long), cudaMemcpyDeviceToHost);
-        cudaMemcpy(ph.data(), f->prog_head[D - 1].phases, ph.size() * sizeof(MPhase), cudaMemcpyDeviceToHost);
-        double sum[5] = {0, 0, 0, 0, 0};
-        int cnt[5] = {0, 0, 0, 0, 0};
-        double wsum[5] = {0, 0, 0, 0, 0};
-        for (size_t i = 0; i < ph.size(); i++) {
-            sum[ph[i].type] += (double)(tr[2 * i + 2] - tr[2 * i]);
-            wsum[ph[i].type] += (double)(tr[2 * i + 1] - tr[2 * i]);
-            cnt[ph[i].type]++;
+    const int head_graph = logits_out ? G_HEAD_LOGITS : G_HEAD;
+    if (!resume) {
+        // prefill: cond tokens, then (start_loc resume) the code tokens of positions < idx_begin  (transformers.py:237-239)
+        const int T0 = cl + idx_begin;
+        if (f->batched_prefill && T0 >= 4 && T0 <= PA_MAXT && (int64_t)B * T0 <= ws.Mmax) {
+            RQB_TRY(prefill_batched(*f, ws, T0, st));
+            // state.idx must equal idx_begin for the first head graph
+            if (idx_begin > 0) RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), (size_t)0, st, false, ws.state, 0, idx_begin, 0));
+        } else {
+            // one cached step each -- causal, so identical to the batched form
+            for (int s = 0; s < cl; s++) RQB_TRY(run(G_COND));
+            // state.idx must equal (position whose codes feed the body) + 1 while replaying the code-token graph
+            for (int j = 1; j <= idx_begin; j++) {
+                RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), (size_t)0, st, false, ws.state, 0, 1, 0));
+                RQB_TRY(run(G_CODE));
+            }
         }
-        const char* nm[5] = {"LN", "GEMM", "ATTN", "CODESUM", "ACT"};
-        for (int k = 0; k < 5; k++)
-            if (cnt[k]) fprintf(stderr, "[mega trace] %-8s n=%3d avg %.2f us (CTA0 own work %.2f us, barrier wait %.2f us)\n", nm[k], cnt[k],
-                                sum[k] / cnt[k] / 1e3, wsum[k] / cnt[k] / 1e3, (sum[k] - wsum[k]) / cnt[k] / 1e3);
-        for (size_t i = 0; i < ph.size() && i < 16; i++)
-            fprintf(stderr, "[mega trace] phase %2zu type %d N_out %5d K %5d splits %2d : %.2f us (work %.2f)\n", i, ph[i].type, ph[i].N_out,
-                    ph[i].K, ph[i].splits, (double)(tr[2 * i + 2] - tr[2 * i]) / 1e3, (double)(tr[2 * i + 1] - tr[2 * i]) / 1e3);
+    }
+    for (int idx = idx_begin; idx < idx_end; idx++) {
+        if (idx > idx_begin || resume) RQB_TRY(run(G_CODE));   // body step on the token of position idx-1 (state.idx == idx)
+        RQB_TRY(run(head_graph));                              // D head steps + sampling; advances idx, step
     }
     return 0;
+}
+
+int ar_fast_trace(ArFast* f, long long* out_host, int cap_launches, char* names, int names_cap) {
+    if (!f || !f->trace || !f->tr_base) return 0;
+    const int n = std::min(cap_launches, TR_CAP);
+    if (cudaMemcpy(out_host, f->tr_base, (size_t)n * 4 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    std::string all;
+    for (int i = 0; i < n; i++) {
+        all += i < (int)f->tr_names.size() ? f->tr_names[i] : "";
+        all += '\n';
+    }
+    if (names && names_cap > 0) {
+        const size_t k = std::min(all.size(), (size_t)names_cap - 1);
+        memcpy(names, all.data(), k);
+        names[k] = 0;
+    }
+    return n;
 }
 
 }  // namespace rqb

@@ -1,12 +1,13 @@
 // P3 "fast" tier workhorse -- weight-streaming skinny GEMM on tcgen05 tensor cores.
 //
-//   D[n, b] = sum_k W[n, k] * X[b, k]            W: [N_out, K] bf16 (nn.Linear layout), X: [B, K] bf16, D fp32 in TMEM
+//   D[n, b] = sum_k W[n, k] * X[b, k]            W: [N_out, K] (nn.Linear layout), X: [B, K], both fp16 or both bf16
+//                                                (GemmTcParams.fmt; the reference's amp class is fp16), D fp32 in TMEM
 //
 // Replaces every nn.Linear of the cached AR step (reference: attentions.py:69-71,99,117-122; transformers.py:94) at
 // M = batch rows.  At B <= 256 these GEMMs are HBM-bound on the *weights* (SURVEY.md finding 5), so the kernel is laid
 // out as a weight streamer with the operands SWAPPED: the weight tile is the UMMA "A" operand (M = 128 output features
 // per CTA, K-major -- exactly the [out,in] row-major layout checkpoints already have, no transpose), the activations are
-// the "B" operand (N = batch padded to 16).  One elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 TMEM);
+// the "B" operand (N = batch padded to 16).  One elected thread issues tcgen05.mma (128 x BN x 16, kind::f16 -> fp32 TMEM);
 // weights and activations arrive through TMA (SWIZZLE_128B, 64-element K slabs) into a STAGES-deep mbarrier ring.
 //
 // Programmatic dependent launch: weight tiles do not depend on the previous kernel, so the producer warp fills the ring
@@ -15,7 +16,11 @@
 //
 // Split-K (blockIdx.x = tile * splits + split) spreads the N_out/128 tiles of the narrow GEMMs (proj, fc2: 12 tiles at
 // E = 1536) over all 148 SMs; partial tiles go to an fp32 workspace [split][B][N_out] and are summed in a FIXED order by
-// the consumer kernel (ln_reduce) -> deterministic, no atomics.
+// the consumer kernel (ln_reduce / attn_fast / act_reduce) -> deterministic, no atomics.  (A form that reduced inside this kernel --
+// partial tiles to L2, one arrival counter per tile, each split CTA reducing its slice of the rows -- was built and measured in
+// round 2: an in-kernel barrier costs what a kernel boundary costs and GEMM-after-GEMM loses the weight prefetch; 249 vs 194 ms.)
+//
+// More activation rows than one UMMA N (256) -- batched prefill, teacher-forced forward -- run as gridDim.y row chunks of BN.
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <cudaTypedefs.h>
@@ -68,132 +73,76 @@ int make_tmap_4d_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W
 }
 
 constexpr int GT_THREADS = 192;
-constexpr int GT_A_BYTES = 128 * 64 * 2;     // 128 output features x 64 k, bf16
+constexpr int GT_A_BYTES = 128 * 64 * 2;     // 128 output features x 64 k, 16-bit
 
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// CL == true: the `splits` CTAs of one output tile form a thread-block cluster; instead of writing fp32 partials to global
-// memory they stage them in their own shared memory, and after a cluster barrier CTA r sums rows [r*rp, (r+1)*rp) of the
-// tile over all peers through distributed shared memory (fixed peer order -> deterministic) and applies the epilogue.
-// Removes the partial round trip through L2 and the reduction work from the consumer kernel.
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t dsmem_map(uint32_t local_addr, uint32_t rank) {
-    uint32_t ra;
-    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
-    return ra;
-}
-// not volatile / no memory clobber on purpose: the S loads of one element are independent and must be allowed to overlap;
-// ordering against the producers' stores is provided by the cluster barriers around the reduction
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
-    float v;
-    asm("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
-    return v;
-}
-
-// ---- GT_GR tail, executed by the 128 epilogue threads (warps 2..5; `ew` = 0..3) after they have stored their partial tile.
-__device__ __forceinline__ unsigned gr_ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void gr_bar_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ float gr_warp_sum(float v) {
+template <int BN, int MODE, bool FULL>
+__device__ __forceinline__ void gt_epilogue_cols(const GemmTcParams& p, uint32_t taddr, bool nvalid, float bias, const float* res,
+                                                 int64_t res_ld, int rdiv, float* out_f, h16* out_h, int64_t ld, int m0, int nb) {
+    // issue the TMEM loads of up to 64 columns back to back, wait once
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 64) {
+        uint32_t r4[4][16];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__device__ __noinline__ void gr_reduce_tail(const GemmTcParams& p, int tile, int split, int ew, int lane) {
-    const int S = p.splits;
-    // 1. publish this CTA's partial tile, wait for the S - 1 peers of the tile.  One gpu-scope release by one thread AFTER the
-    //    CTA barrier covers every epilogue thread's stores (release is cumulative over what the barrier ordered before it) --
-    //    the pattern of a cooperative-groups grid sync; no per-thread fence.
-    gr_bar_epilogue();
-    if (ew == 0 && lane == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.gr_counter + tile), "r"(1u) : "memory");
-        const long long t0 = clock64();
-        while (gr_ld_acquire(p.gr_counter + tile) < (unsigned)S) {
-            if (clock64() - t0 > (1ll << 32)) __trap();      // > 2 s: the grid is not co-resident (see GemmTcParams) -- fail, do not hang
+        for (int c = 0; c < 4; c++)
+            if (cb + c * 16 < BN) tc::tmem_ld16(taddr + (uint32_t)(cb + c * 16), r4[c]);
+        tc::tmem_ld_wait();
+        if (nvalid) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (cb + c * 16 < BN) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int col = cb + c * 16 + i;                    // activation row m0 + col
+                        if (FULL || col < nb) {
+                            float v = __uint_as_float(r4[c][i]);
+                            if (MODE != GT_PARTIAL) v += bias;
+                            if (MODE == GT_F32 && res != nullptr)
+                                v += res[(rdiv ? (int64_t)((m0 + col) / rdiv) : (int64_t)(m0 + col)) * res_ld];
+                            if (MODE == GT_PARTIAL || MODE == GT_F32) out_f[(int64_t)col * ld] = v;
+                            else if (MODE == GT_H16) out_h[(int64_t)col * ld] = pack_h16(v, p.fmt);
+                            else out_h[(int64_t)col * ld] = pack_h16(gelu_erf_f(v), p.fmt);
+                        }
+                    }
+                }
+            }
         }
     }
-    gr_bar_epilogue();
-    // 2. reduce rows [r0, r1) of the tile: warp <-> row (stride 4), lane <-> 4 consecutive output features
-    const int rp = (p.B + S - 1) / S;
-    const int r0 = split * rp, r1 = (r0 + rp) < p.B ? (r0 + rp) : p.B;
-    const float* sc = p.gr_scratch + (int64_t)tile * S * p.B * 128;
-    const int n0 = tile * 128 + 4 * lane;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) {
-        bias4 = *reinterpret_cast<const float4*>(p.bias + n0);
-        bias4.x *= p.bias_scale; bias4.y *= p.bias_scale; bias4.z *= p.bias_scale; bias4.w *= p.bias_scale;
-    }
-    float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.gr_stats_in) c4 = *reinterpret_cast<const float4*>(p.gr_fold_c + n0);
+}
+
+// Epilogue of one thread: accumulator columns [0, BN) of TMEM lane `taddr` = output feature n for the activation rows
+// m0 .. m0 + nb - 1.  One warp per scheduler here, so the instruction stream is kept short and branch-free: the mode is a
+// template parameter, row addresses are base + constant * stride, and the row bound is checked only for ragged chunks.
+template <int BN, int MODE>
+__device__ __forceinline__ void gt_epilogue(const GemmTcParams& p, uint32_t taddr, int n, int split, int m0, int nb) {
+    const bool nvalid = n < p.N_out;
+    const float bias = (MODE != GT_PARTIAL && p.bias != nullptr && nvalid) ? p.bias[n] * p.bias_scale : 0.f;
     const float* res = nullptr;
-    if (p.gr_kind == 0 && p.residual != nullptr) res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0);
-    const int nst = p.K / 128;
-    for (int r = r0 + ew; r < r1; r += 4) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < S; s0 += 8) {
-            float4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (s0 + i < S) v[i] = __ldcg(reinterpret_cast<const float4*>(sc + ((int64_t)(s0 + i) * p.B + r) * 128) + lane);
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (s0 + i < S) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }   // fixed order
-        }
-        if (p.gr_stats_in) {
-            // LayerNorm statistics of input row r from its per-tile (sum, M2) pairs (Chan's parallel combination)
-            float s1 = 0.f;
-            for (int t = lane; t < nst; t += 32) s1 += __ldcg(p.gr_stats_in + (int64_t)r * nst + t).x;
-            const float mean = gr_warp_sum(s1) / (float)p.K;
-            float m2 = 0.f;
-            for (int t = lane; t < nst; t += 32) {
-                const float2 st = __ldcg(p.gr_stats_in + (int64_t)r * nst + t);
-                const float d = st.x * (1.0f / 128.0f) - mean;
-                m2 += st.y + 128.0f * d * d;
-            }
-            const float rstd = rsqrtf(gr_warp_sum(m2) / (float)p.K + 1e-5f);
-            acc.x = rstd * (acc.x - mean * c4.x); acc.y = rstd * (acc.y - mean * c4.y);
-            acc.z = rstd * (acc.z - mean * c4.z); acc.w = rstd * (acc.w - mean * c4.w);
-        }
-        acc.x += bias4.x; acc.y += bias4.y; acc.z += bias4.z; acc.w += bias4.w;
-        if (p.gr_kind == 1) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(gelu_erf_f(acc.x), gelu_erf_f(acc.y));
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(gelu_erf_f(acc.z), gelu_erf_f(acc.w));
-            uint2 pk;
-            pk.x = *reinterpret_cast<unsigned*>(&h0);
-            pk.y = *reinterpret_cast<unsigned*>(&h1);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)r * p.ld_out + n0) = pk;
-        } else {
-            if (res) {
-                const float4 rr = __ldcg(reinterpret_cast<const float4*>(res + (int64_t)r * p.ld_res + n0));
-                acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w;
-            }
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (int64_t)r * p.ld_out + n0) = acc;
-            if (p.gr_out_bf16) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<unsigned*>(&h0);
-                pk.y = *reinterpret_cast<unsigned*>(&h1);
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.gr_out_bf16) + (int64_t)r * p.ld_out + n0) = pk;
-            }
-            if (p.gr_stats_out) {
-                const float s1 = gr_warp_sum((acc.x + acc.y) + (acc.z + acc.w));
-                const float tm = s1 * (1.0f / 128.0f);
-                const float d0 = acc.x - tm, d1 = acc.y - tm, d2 = acc.z - tm, d3 = acc.w - tm;
-                const float m2 = gr_warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
-                if (lane == 0) p.gr_stats_out[(int64_t)r * (p.N_out / 128) + tile] = make_float2(s1, m2);
-            }
-        }
+    int64_t res_ld = 0;
+    if (MODE == GT_F32 && p.residual != nullptr && nvalid) {
+        res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0) + n;
+        res_ld = p.ld_res;
     }
+    const int rdiv = p.res_div > 1 ? p.res_div : 0;                 // 0: residual row == activation row
+    float* out_f = nullptr;
+    h16* out_h = nullptr;
+    int64_t ld = 0;
+    if (MODE == GT_PARTIAL) {
+        out_f = p.partial + ((int64_t)split * p.B + m0) * p.N_out + n;
+        ld = p.N_out;
+    } else if (MODE == GT_F32) {
+        out_f = reinterpret_cast<float*>(p.out) + (int64_t)m0 * p.ld_out + n;
+        ld = p.ld_out;
+    } else {
+        out_h = reinterpret_cast<h16*>(p.out) + (int64_t)m0 * p.ld_out + n;
+        ld = p.ld_out;
+    }
+    if (nb == BN) gt_epilogue_cols<BN, MODE, true>(p, taddr, nvalid, bias, res, res_ld, rdiv, out_f, out_h, ld, m0, nb);
+    else gt_epilogue_cols<BN, MODE, false>(p, taddr, nvalid, bias, res, res_ld, rdiv, out_f, out_h, ld, m0, nb);
 }
 
-template <int BN, int STAGES, bool CL, bool GR = false>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(GT_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, GemmTcParams p) {
     constexpr int B_BYTES = BN * 64 * 2;
@@ -208,22 +157,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+    const int m0 = blockIdx.y * BN;                  // first activation row of this CTA's chunk
     const int nkb_total = p.K / 64;
     const int kb0 = (int)((int64_t)nkb_total * split / p.splits), kb1 = (int)((int64_t)nkb_total * (split + 1) / p.splits);
     const int nkb = kb1 - kb0;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
     tc::pdl_launch_dependents();             // let the next kernel of the chain start its own weight prefetch
     if (warp == 0 && lane == 0) {
+        if (tr) p.trace[0] = tc::gtimer();
         tc::prefetch_tmap(&tmW);
         tc::prefetch_tmap(&tmX);
         for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) {
-        tc::tmem_alloc(tmem_slot, TMEM_COLS);
-        if (p.relinq) tc::tmem_relinquish();
-    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);     // (also relinquishes the allocation permit: co-resident CTAs do not wait)
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -233,30 +182,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         if (lane == 0) {
             // ---- TMA producer.  Weights first (independent of the upstream kernel), then wait, then activations.
             const int pre = nkb < STAGES ? nkb : STAGES;
+            // streamed once (M <= 256: evict first) or shared by every row chunk of a large-M launch (keep in L2)
+            const uint64_t w_hint = gridDim.y > 1 ? tc::L2_EVICT_LAST : tc::L2_EVICT_FIRST;
             for (int i = 0; i < pre; i++) {
                 tc::mbar_expect_tx(&full[i], STAGE_BYTES);
-                tc::tma_load_2d(smem + i * STAGE_BYTES, &tmW, &full[i], p.w_tiled ? 0 : (kb0 + i) * 64,
-                                p.w_tiled ? (tile * nkb_total + kb0 + i) * 128 : tile * 128, tc::L2_EVICT_FIRST);
+                tc::tma_load_2d(smem + i * STAGE_BYTES, &tmW, &full[i], (kb0 + i) * 64, tile * 128, w_hint);
             }
             if (p.l2pf)
-                for (int i = pre; i < nkb; i++)
-                    tc::tma_prefetch_2d(&tmW, p.w_tiled ? 0 : (kb0 + i) * 64,
-                                        p.w_tiled ? (tile * nkb_total + kb0 + i) * 128 : tile * 128);
+                for (int i = pre; i < nkb; i++) tc::tma_prefetch_2d(&tmW, (kb0 + i) * 64, tile * 128);
             tc::pdl_wait();
+            if (tr) p.trace[1] = tc::gtimer();
             for (int i = 0; i < pre; i++)
-                tc::tma_load_2d(smem + i * STAGE_BYTES + GT_A_BYTES, &tmX, &full[i], (kb0 + i) * 64, 0, tc::L2_EVICT_LAST);
+                tc::tma_load_2d(smem + i * STAGE_BYTES + GT_A_BYTES, &tmX, &full[i], (kb0 + i) * 64, m0, tc::L2_EVICT_LAST);
+            if (p.next_w != nullptr) {
+                const int64_t ctas = (int64_t)gridDim.x * gridDim.y, me = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+                const int64_t per = ((p.next_w_bytes + ctas - 1) / ctas + 127) & ~(int64_t)127;
+                const int64_t b0 = me * per, b1 = (b0 + per) < p.next_w_bytes ? (b0 + per) : p.next_w_bytes;
+                for (int64_t o = b0; o < b1; o += 16384) {
+                    const int64_t nbytes = (b1 - o) < 16384 ? (b1 - o) : 16384;
+                    tc::bulk_prefetch_l2(reinterpret_cast<const char*>(p.next_w) + o, (uint32_t)(nbytes & ~(int64_t)15));
+                }
+            }
             for (int i = pre; i < nkb; i++) {
                 const int s = i % STAGES;
                 tc::mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
                 tc::mbar_expect_tx(&full[s], STAGE_BYTES);
-                tc::tma_load_2d(smem + s * STAGE_BYTES, &tmW, &full[s], p.w_tiled ? 0 : (kb0 + i) * 64,
-                                p.w_tiled ? (tile * nkb_total + kb0 + i) * 128 : tile * 128, tc::L2_EVICT_FIRST);
-                tc::tma_load_2d(smem + s * STAGE_BYTES + GT_A_BYTES, &tmX, &full[s], (kb0 + i) * 64, 0, tc::L2_EVICT_LAST);
+                tc::tma_load_2d(smem + s * STAGE_BYTES, &tmW, &full[s], (kb0 + i) * 64, tile * 128, w_hint);
+                tc::tma_load_2d(smem + s * STAGE_BYTES + GT_A_BYTES, &tmX, &full[s], (kb0 + i) * 64, m0, tc::L2_EVICT_LAST);
             }
         }
     } else if (warp == 1) {
         // ---- MMA issuer
-        constexpr uint32_t idesc = tc::umma_idesc(128, BN, 1 /*bf16*/);
+        const uint32_t idesc = tc::umma_idesc(128, BN, p.fmt);
         for (int i = 0; i < nkb; i++) {
             const int s = i % STAGES;
             tc::mbar_wait(&full[s], (i / STAGES) & 1);
@@ -279,238 +236,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const int n = tile * 128 + q * 32 + lane;
         tc::mbar_wait(tmem_full, 0);
         tc::tc_fence_after();
-        const bool nvalid = n < p.N_out;
-        if (CL) {
-            float* stg = reinterpret_cast<float*>(smem);                    // [128][BN + 1] fp32, over the drained ring
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[16];
-                tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; i++) stg[(q * 32 + lane) * (BN + 1) + c0 + i] = __uint_as_float(r[i]);
-            }
-        } else {
-        const float bias = (p.bias != nullptr && nvalid && p.mode != GT_PARTIAL && !GR) ? p.bias[n] * p.bias_scale : 0.f;
-        const float* res = nullptr;
-        if (p.mode == GT_F32 && p.residual != nullptr)
-            res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0);
-        // issue the TMEM loads of up to 64 columns back to back, wait once
-#pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 64) {
-            uint32_t r4[4][16];
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (cb + c * 16 < BN) tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb + c * 16), r4[c]);
-            tc::tmem_ld_wait();
-            if (!nvalid) continue;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-            const int c0 = cb + c * 16;
-            if (c0 >= BN) break;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int b = c0 + i;
-                if (b >= p.B) break;
-                float v = __uint_as_float(r4[c][i]) + bias;
-                if constexpr (GR) {      // group-reduce instantiation: the partial tile goes to the tile-major L2 scratch
-                    __stcg(p.gr_scratch + (((int64_t)tile * p.splits + split) * p.B + b) * 128 + (q * 32 + lane), v);
-                    continue;
-                }
-                switch (p.mode) {
-                    case GT_F32:
-                        if (res) v += res[(int64_t)b * p.ld_res + n];
-                        reinterpret_cast<float*>(p.out)[(int64_t)b * p.ld_out + n] = v;
-                        break;
-                    case GT_BF16:
-                        reinterpret_cast<__nv_bfloat16*>(p.out)[(int64_t)b * p.ld_out + n] = __float2bfloat16(v);
-                        break;
-                    case GT_BF16_GELU:
-                        reinterpret_cast<__nv_bfloat16*>(p.out)[(int64_t)b * p.ld_out + n] = __float2bfloat16(gelu_erf_f(v));
-                        break;
-                    case GT_PARTIAL:
-                        p.partial[((int64_t)split * p.B + b) * p.N_out + n] = v;
-                        break;
-                    default:
-                        break;
-                }
-            }
-            }
+        if (tr && warp == 2 && lane == 0) p.trace[2] = tc::gtimer();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int nb = (p.B - m0) < BN ? (p.B - m0) : BN;          // valid activation rows of this chunk
+        switch (p.mode) {
+            case GT_PARTIAL: gt_epilogue<BN, GT_PARTIAL>(p, taddr, n, split, m0, nb); break;
+            case GT_F32: gt_epilogue<BN, GT_F32>(p, taddr, n, split, m0, nb); break;
+            case GT_H16: gt_epilogue<BN, GT_H16>(p, taddr, n, split, m0, nb); break;
+            default: gt_epilogue<BN, GT_H16_GELU>(p, taddr, n, split, m0, nb); break;
         }
-        if constexpr (GR) gr_reduce_tail(p, tile, split, warp - 2, lane);
-        }
-    }
-    if (CL) {
-        __syncwarp();
-        cluster_sync_all();                                                 // every CTA of the tile has staged its partial
-        tc::pdl_wait();
-        const int S = p.splits, rp = (128 + S - 1) / S;
-        const int r0 = split * rp, r1 = (r0 + rp) < 128 ? (r0 + rp) : 128;
-        const uint32_t stg_u32 = tc::smem_u32(smem);
-        const float* res = nullptr;
-        if (p.mode == GT_F32 && p.residual != nullptr)
-            res = p.residual + (p.res_row_ptr ? (int64_t)(*p.res_row_ptr) * p.res_row_stride : 0);
-        const int total = (r1 - r0) * p.B;
-        uint32_t peer[8];
-#pragma unroll
-        for (int pr = 0; pr < 8; pr++) peer[pr] = dsmem_map(stg_u32, (uint32_t)(pr < S ? pr : 0));
-        for (int idx = threadIdx.x; idx < total; idx += GT_THREADS) {
-            // consecutive threads -> consecutive output features (coalesced stores); b is the slow index
-            const int row = r0 + idx % (r1 - r0), b = idx / (r1 - r0);
-            const int n = tile * 128 + row;
-            const uint32_t off = (uint32_t)(row * (BN + 1) + b) * 4u;
-            float part[8];
-#pragma unroll
-            for (int pr = 0; pr < 8; pr++) part[pr] = pr < S ? ld_dsmem_f32(peer[pr] + off) : 0.f;
-            float v = 0.f;
-#pragma unroll
-            for (int pr = 0; pr < 8; pr++) v += part[pr];                       // fixed order: deterministic
-            if (p.bias) v += p.bias[n] * p.bias_scale;
-            if (p.mode == GT_F32) {
-                if (res) v += res[(int64_t)b * p.ld_res + n];
-                reinterpret_cast<float*>(p.out)[(int64_t)b * p.ld_out + n] = v;
-            } else if (p.mode == GT_BF16_GELU) {
-                reinterpret_cast<__nv_bfloat16*>(p.out)[(int64_t)b * p.ld_out + n] = __float2bfloat16(gelu_erf_f(v));
-            } else {
-                reinterpret_cast<__nv_bfloat16*>(p.out)[(int64_t)b * p.ld_out + n] = __float2bfloat16(v);
-            }
-        }
-        __syncwarp();
-        cluster_sync_all();                                                 // peers may still be reading this CTA's staging area
+        if (tr && warp == 2 && lane == 0) p.trace[3] = tc::gtimer();
     }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES, bool CL, bool GR = false>
+template <int BN, int STAGES>
 static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (GT_A_BYTES + BN * 128) + 1024 + 256;
-    static_assert(!CL || (size_t)STAGES * (GT_A_BYTES + BN * 128) >= (size_t)128 * (BN + 1) * 4, "staging area must fit in the ring");
-    RQB_ENSURE_SMEM(smem, gemm_tc_kernel<BN, STAGES, CL, GR>);
+    RQB_ENSURE_SMEM(smem, gemm_tc_kernel<BN, STAGES>);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(ceil_div(p.N_out, 128) * p.splits));
+    cfg.gridDim = dim3((unsigned)(ceil_div(p.N_out, 128) * p.splits), (unsigned)ceil_div(p.B, BN));
     cfg.blockDim = dim3(GT_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (CL) {
-        at[1].id = cudaLaunchAttributeClusterDimension;
-        at[1].val.clusterDim.x = (unsigned)p.splits;
-        at[1].val.clusterDim.y = 1;
-        at[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
-    }
-    RQB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, CL, GR>, tmW, tmX, p));
+    RQB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES>, tmW, tmX, p));
     g_launches++;
     return 0;
 }
 
-int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p_in, bool pdl, cudaStream_t st) {
-    GemmTcParams p = p_in;
-    if (const char* e = getenv("RQB200_GEMM_L2PF")) p.l2pf = atoi(e);
-    if (const char* e = getenv("RQB200_GEMM_RELINQ")) p.relinq = atoi(e);
+// ring depth: `deep` = the deepest ring that fits (one CTA per SM, the whole K slice of a split prefetched ahead of the upstream
+// kernel); otherwise half of it, so that two CTAs of consecutive launches share an SM.  Same k order -> same bits either way.
+int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
     if (p.K % 64 != 0 || p.N_out % 128 != 0) return fail(RQB200_EINVAL, "gemm_tc: need K % 64 == 0 and N_out % 128 == 0");
-    if (p.B < 1 || p.B > 256) return fail(RQB200_EINVAL, "gemm_tc: batch rows must be in [1,256]");
+    if (p.B < 1) return fail(RQB200_EINVAL, "gemm_tc: no activation rows");
     if (p.splits < 1 || p.splits > p.K / 64) return fail(RQB200_EINVAL, "gemm_tc: bad split count");
+    if (p.fmt != 0 && p.fmt != 1) return fail(RQB200_EINVAL, "gemm_tc: fmt must be 0 (fp16) or 1 (bf16)");
     const int bn = gemm_tc_bn(p.B);
-    if (p.mode == GT_GR && (p.gr_scratch == nullptr || p.gr_counter == nullptr || p.ld_out % 4 != 0 || (p.gr_stats_in && p.K % 128 != 0)))
-        return fail(RQB200_EINVAL, "gemm_tc: GT_GR needs scratch, counters, ld_out % 4 == 0 (and K % 128 == 0 with a folded LayerNorm)");
-    if (p.mode == GT_GR) {
-        switch (bn) {
-            case 16: return launch_gemm_tc_t<16, 8, false, true>(tmW, tmX, p, pdl, st);
-            case 32: return launch_gemm_tc_t<32, 8, false, true>(tmW, tmX, p, pdl, st);
-            case 64: return launch_gemm_tc_t<64, 8, false, true>(tmW, tmX, p, pdl, st);
-            case 128: return launch_gemm_tc_t<128, 6, false, true>(tmW, tmX, p, pdl, st);
-            default: return launch_gemm_tc_t<256, 4, false, true>(tmW, tmX, p, pdl, st);
-        }
-    }
-    if (p.splits > 1 && p.mode != GT_PARTIAL) {          // split-K with an in-kernel (cluster / DSMEM) reduction
-        if (p.splits > 8) return fail(RQB200_EINVAL, "gemm_tc: cluster split-K supports at most 8 splits");
-        switch (bn) {
-            case 16: return launch_gemm_tc_t<16, 8, true>(tmW, tmX, p, pdl, st);
-            case 32: return launch_gemm_tc_t<32, 8, true>(tmW, tmX, p, pdl, st);
-            case 64: return launch_gemm_tc_t<64, 8, true>(tmW, tmX, p, pdl, st);
-            case 128: return launch_gemm_tc_t<128, 6, true>(tmW, tmX, p, pdl, st);
-            default: return launch_gemm_tc_t<256, 4, true>(tmW, tmX, p, pdl, st);
-        }
-    }
-    // RQB200_GEMM_STAGES (experiment): a shallower ring lets 2-3 GEMM CTAs of consecutive launches share an SM, so the
-    // next GEMM of the PDL chain prefetches its weights while the current one still runs.  Same k order -> same bits.
-    int stages = 8;
-    if (const char* e = getenv("RQB200_GEMM_STAGES")) stages = atoi(e);
-    if (bn <= 64 && stages != 8) {
-        if (bn == 64) {
-            if (stages == 3) return launch_gemm_tc_t<64, 3, false>(tmW, tmX, p, pdl, st);
-            if (stages == 4) return launch_gemm_tc_t<64, 4, false>(tmW, tmX, p, pdl, st);
-            if (stages == 6) return launch_gemm_tc_t<64, 6, false>(tmW, tmX, p, pdl, st);
-        } else if (bn == 32) {
-            if (stages == 3 || stages == 4) return launch_gemm_tc_t<32, 4, false>(tmW, tmX, p, pdl, st);
-        } else {
-            if (stages == 3 || stages == 4) return launch_gemm_tc_t<16, 4, false>(tmW, tmX, p, pdl, st);
-        }
-    }
+    if (p.B > 256 && p.mode == GT_PARTIAL) return fail(RQB200_EINVAL, "gemm_tc: split-K takes at most 256 activation rows");
+    if (p.mode != GT_PARTIAL && p.splits != 1) return fail(RQB200_EINVAL, "gemm_tc: direct epilogues need splits == 1");
+    const bool deep = p.deep != 0;
     switch (bn) {
-        case 16: return launch_gemm_tc_t<16, 8, false>(tmW, tmX, p, pdl, st);
-        case 32: return launch_gemm_tc_t<32, 8, false>(tmW, tmX, p, pdl, st);
-        case 64: return launch_gemm_tc_t<64, 8, false>(tmW, tmX, p, pdl, st);
-        case 128: return launch_gemm_tc_t<128, 6, false>(tmW, tmX, p, pdl, st);
-        default: return launch_gemm_tc_t<256, 4, false>(tmW, tmX, p, pdl, st);
+        case 16: return deep ? launch_gemm_tc_t<16, 8>(tmW, tmX, p, pdl, st) : launch_gemm_tc_t<16, 4>(tmW, tmX, p, pdl, st);
+        case 32: return deep ? launch_gemm_tc_t<32, 8>(tmW, tmX, p, pdl, st) : launch_gemm_tc_t<32, 4>(tmW, tmX, p, pdl, st);
+        case 64: return deep ? launch_gemm_tc_t<64, 8>(tmW, tmX, p, pdl, st) : launch_gemm_tc_t<64, 4>(tmW, tmX, p, pdl, st);
+        case 128: return deep ? launch_gemm_tc_t<128, 6>(tmW, tmX, p, pdl, st) : launch_gemm_tc_t<128, 3>(tmW, tmX, p, pdl, st);
+        default: return deep ? launch_gemm_tc_t<256, 4>(tmW, tmX, p, pdl, st) : launch_gemm_tc_t<256, 2>(tmW, tmX, p, pdl, st);
     }
 }
 
-// weight tensor map: row-major [N_out, K], or tile-major [N_out/128][K/64][128][64] viewed as a 64-wide 2-D tensor
-int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K, bool tiled) {
-    if (tiled) return make_tmap_2d(out, W, 1, 64, (uint64_t)(N_out / 128) * (K / 64) * 128, 128, 64, 128);
+// weight tensor map: row-major [N_out, K] 16-bit, box = 64 k x 128 rows
+int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K) {
     return make_tmap_2d(out, W, 1, (uint64_t)K, (uint64_t)N_out, (uint64_t)K * 2, 64, 128);
 }
 
 }  // namespace rqb
 
-// ---- diagnostic entry point (tests/test_gpu_tc.py): one GEMM through the tcgen05 kernel
+// ---- diagnostic entry points (tests/test_gpu_tc.py, bench.py's roofline leg): one GEMM through the tcgen05 kernel
 
-extern "C" int rqb200_dbg_gemm_tc(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out,
-                                  int out_is_bf16, int gelu, float* partial, int N_out, int K, int B, int splits,
+extern "C" int rqb200_dbg_gemm_tc(const void* W16, const void* X16, const float* bias, const float* residual, void* out,
+                                  int out_is_16, int gelu, float* partial, int N_out, int K, int B, int splits, int fmt,
                                   void* stream) {
     using namespace rqb;
     CUtensorMap tw, tx;
     const int bn = gemm_tc_bn(B);
-    // splits < 0: W is tile-major ([N_out/128][K/64][128][64]) and |splits| is the split count
-    const bool tiled = splits < 0;
-    if (tiled) splits = -splits;
-    RQB_TRY(make_tmap_weight(&tw, W_bf16, N_out, K, tiled));
-    RQB_TRY(make_tmap_2d(&tx, X_bf16, 1, (uint64_t)K, (uint64_t)B, (uint64_t)K * 2, 64, (uint32_t)bn));
+    RQB_TRY(make_tmap_weight(&tw, W16, N_out, K));
+    RQB_TRY(make_tmap_2d(&tx, X16, 1, (uint64_t)K, (uint64_t)B, (uint64_t)K * 2, 64, (uint32_t)bn));
     GemmTcParams p = {};
-    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits;
+    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits; p.fmt = fmt; p.deep = 1;
     p.bias = bias; p.bias_scale = 1.f; p.residual = residual; p.ld_res = N_out; p.out = out; p.ld_out = N_out; p.partial = partial;
-    p.w_tiled = tiled ? 1 : 0;
-    p.mode = (splits > 1 && partial != nullptr) ? GT_PARTIAL : (out_is_bf16 ? (gelu ? GT_BF16_GELU : GT_BF16) : GT_F32);
-    return launch_gemm_tc(tw, tx, p, false, (cudaStream_t)stream);
-}
-
-// one GT_GR launch (split-K with the in-kernel group reduction); scratch >= splits*B*N_out floats, counters >= N_out/128 (zeroed here)
-extern "C" int rqb200_dbg_gemm_gr(const void* W_bf16, const void* X_bf16, const float* bias, const float* residual, void* out, int kind,
-                                  float* scratch, unsigned* counters, void* out_bf16, float* stats_out, const float* stats_in,
-                                  const float* fold_c, int N_out, int K, int B, int splits, void* stream) {
-    using namespace rqb;
-    CUtensorMap tw, tx;
-    const int bn = gemm_tc_bn(B);
-    RQB_TRY(make_tmap_weight(&tw, W_bf16, N_out, K, false));
-    RQB_TRY(make_tmap_2d(&tx, X_bf16, 1, (uint64_t)K, (uint64_t)B, (uint64_t)K * 2, 64, (uint32_t)bn));
-    int dev = 0, n_sm = 0;
-    RQB_CUDA(cudaGetDevice(&dev));
-    RQB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    if ((N_out / 128) * splits > n_sm) return fail(RQB200_EINVAL, "dbg_gemm_gr: the grid would not be co-resident");
-    RQB_CUDA(cudaMemsetAsync(counters, 0, (size_t)(N_out / 128) * sizeof(unsigned), (cudaStream_t)stream));
-    GemmTcParams p = {};
-    p.N_out = N_out; p.K = K; p.B = B; p.splits = splits; p.mode = GT_GR;
-    p.bias = bias; p.bias_scale = 1.f; p.residual = kind == 0 ? residual : nullptr; p.ld_res = N_out; p.out = out; p.ld_out = N_out;
-    p.gr_scratch = scratch; p.gr_counter = counters; p.gr_kind = kind; p.gr_out_bf16 = out_bf16;
-    p.gr_stats_out = reinterpret_cast<float2*>(stats_out); p.gr_stats_in = reinterpret_cast<const float2*>(stats_in);
-    p.gr_fold_c = fold_c;
+    p.mode = (splits > 1 || partial != nullptr) ? GT_PARTIAL : (out_is_16 ? (gelu ? GT_H16_GELU : GT_H16) : GT_F32);
+    if (p.mode == GT_PARTIAL && partial == nullptr) return fail(RQB200_EINVAL, "dbg_gemm_tc: splits > 1 needs a partial buffer");
     return launch_gemm_tc(tw, tx, p, false, (cudaStream_t)stream);
 }

@@ -7,8 +7,8 @@
 namespace rqb {
 // rq_search.cu
 int launch_rq_quantize(const float* x, const float* cb, int64_t N, int K, int C, int D, int64_t* codes, float* quant_list,
-                       float* resid_out, cudaStream_t st);
-// rq_search2.cu -- 8x8 register tile, codebook streamed in 32-channel slabs, 2-CTA clusters splitting the codebook (RQB200_RQ_V2=1)
+                       float* resid_out, cudaStream_t st, int form = 0);
+// rq_search2.cu -- 8x8 register tile, codebook streamed in 32-channel slabs, 2-CTA clusters splitting the codebook (the default form)
 bool rq_quantize2_supported(int64_t N, int K, int C);
 int launch_rq_quantize2(const float* x, const float* cb, int64_t N, int K, int C, int D, int64_t* codes, float* quant_list,
                         float* resid_out, cudaStream_t st);
@@ -16,7 +16,7 @@ int launch_rq_embed(const int64_t* codes, const float* cb, int64_t N, int D, int
                     cudaStream_t st);
 // sampler.cu
 int launch_sample(const float* logits, const float* q, int B, int V, float temperature, int top_k, float top_p,
-                  int64_t* out_idx, const int64_t* force, int64_t out_stride, cudaStream_t st);
+                  int64_t* out_idx, const int64_t* force, int64_t out_stride, cudaStream_t st, int algo = 1);
 // ar_kernels.cu
 int launch_linear(const float* X, int64_t ldx, const void* W, int wdtype, const float* bias, const float* R, float* Y,
                   int64_t ldy, int M, int N, int K, int act, cudaStream_t st);
@@ -64,9 +64,16 @@ int make_tmap_4d_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W
                       uint32_t box_w, uint32_t box_h, uint32_t box_b);
 
 // gemm_tc.cu -- tcgen05 weight-streaming GEMM (fast tier)
-enum GemmTcMode { GT_F32 = 0, GT_BF16 = 1, GT_BF16_GELU = 2, GT_PARTIAL = 3, GT_GR = 4 };
+enum GemmTcMode { GT_F32 = 0, GT_H16 = 1, GT_H16_GELU = 2, GT_PARTIAL = 3 };
 struct GemmTcParams {
-    int N_out, K, B, splits, mode;
+    int N_out, K, B, splits, mode;   // B = activation rows (batch rows of the cached step, or B*T tokens of a prefill / forward pass)
+    int fmt;                      // 16-bit operand / output format: 0 = fp16 (the reference's autocast class), 1 = bf16
+    int deep;                     // 1: deepest shared-memory ring (one CTA per SM); 0: half depth (two CTAs of consecutive launches per SM)
+    int l2pf;                     // 1: before waiting for the upstream kernel, prefetch into L2 the weight boxes that do not fit the ring
+    // once this launch's own loads are issued, every CTA prefetches its 1/grid share of [next_w, next_w + next_w_bytes) into L2: the
+    // weights of a LATER launch whose own prefetch window is too short (fc2 behind fc1 + act_reduce).  nullable.
+    const void* next_w;
+    int64_t next_w_bytes;
     const float* bias;            // [N_out] (nullable); added as bias * bias_scale
     float bias_scale;
     // GT_F32 only: out = acc + bias + residual[(row0 * res_row_stride) + b * ld_res + n], row0 = res_row_ptr ? *res_row_ptr : 0
@@ -74,27 +81,14 @@ struct GemmTcParams {
     const float* residual;
     int64_t ld_res, res_row_stride;
     const int* res_row_ptr;
-    void* out;                    // [B, ld_out] f32 / bf16
+    int res_div;                  // > 1: activation row b reads residual row b / res_div (token-major prefill rows share a positional row)
+    void* out;                    // [B, ld_out] f32 / 16-bit
     int64_t ld_out;
     float* partial;               // GT_PARTIAL: [splits][B][N_out] f32 (no bias)
-    int w_tiled;                  // 1: W is stored tile-major [N_out/128][K/64][128][64] (each TMA box = 16 KB contiguous in HBM)
-    int l2pf;                     // 1: before waiting for the upstream kernel, prefetch into L2 the weight boxes that do not fit the ring
-    int relinq;                   // 1: tcgen05.relinquish_alloc_permit right after the TMEM allocation (matters once two GEMM CTAs share an SM)
-    // GT_GR ("group reduce"): split-K whose reduction happens INSIDE the kernel.  Every split CTA stores its fp32 partial tile to
-    // gr_scratch (stays in L2), signals the tile's arrival counter, waits for its `splits` peers and then reduces its own slice of
-    // the batch rows in a fixed split order (deterministic) and applies the epilogue -- no separate reduction launch.
-    // All CTAs of the grid must be co-resident (grid <= SMs x occupancy) and no other spinning grid may share the GPU.
-    float* gr_scratch;            // [N_out/128][splits][B][128] f32
-    unsigned* gr_counter;         // [N_out/128], zero before the launch
-    int gr_kind;                  // 0: out f32 [B,ld_out] = sum + bias + residual (+ gr_out_bf16, + gr_stats_out); 1: out bf16 = gelu(sum + bias)
-    void* gr_out_bf16;            // kind 0, nullable: bf16 copy of the new rows [B, ld_out]
-    float2* gr_stats_out;         // kind 0, nullable: [B][N_out/128] (sum, M2 about the tile mean) of the new rows -- LayerNorm statistics
-    // folded LayerNorm on the INPUT rows (weights hold W*diag(gamma), bias holds W*beta + b): v = rstd_b*(sum - mean_b*c_n) + bias_n
-    const float2* gr_stats_in;    // [B][K/128] tile statistics of the input rows, NULL: no fold
-    const float* gr_fold_c;       // [N_out]  c_n = sum_k W'[n,k]
+    long long* trace;             // diagnostics, nullable: 4 globaltimer stamps of CTA 0 (entry, dependency resolved, accumulator ready, done)
 };
 inline int gemm_tc_bn(int B) { return B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : B <= 128 ? 128 : 256; }
-int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K, bool tiled);
+int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K);
 int launch_gemm_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st);
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes_log2, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
@@ -117,45 +111,15 @@ struct StepState {
 };
 int launch_sample_dyn(const float* logits, const StepState* stt, int d, int B, int V, int HW, int D, cudaStream_t st, bool pdl);
 
-enum { MP_LN = 0, MP_GEMM = 1, MP_ATTN = 2, MP_CODESUM = 3, MP_ACT = 4 };
-
-struct alignas(64) MPhase {
-    CUtensorMap tmW, tmX;                 // GEMM operands (W: [N_out,K] bf16 box 64x128; X: [B,K] bf16 box 64x64)
-    int type;
-    // ---- MP_LN: x_out = x_in + bias + sum_s partial[s] (+ extra) ; xn = LN(x_out)
-    const float* x_in; const float* partial; int S; const float* bias; const float* extra; float* x_out;
-    const float* g; const float* be; __nv_bfloat16* xn;
-    // ---- MP_GEMM
-    int N_out, K, splits, mode;           // mode: GT_F32 | GT_BF16_GELU | GT_PARTIAL
-    int w_tiled;
-    const float* gbias; float bias_scale;
-    const float* res; const int* res_row_ptr; long long res_row_stride, ld_res;
-    void* out; float* gpartial;
-    // ---- MP_ATTN
-    const float* apart; int aS; const float* bqkv; __nv_bfloat16 *kc, *vc, *att; int Tmax; const int* t_ptr; int t_host;
-    // ---- MP_CODESUM
-    int cs_mode; __nv_bfloat16* cs_out;
-};
-
-struct MegaParams {
-    const MPhase* phases;
-    int n_phases;
-    int B, E, nh;
-    unsigned* bar;                        // [0] monotonic arrive counter, [1] base for the next launch
-    const StepState* stt;
-    const float* codebook; int HW, D, Kc, C;
-    long long* trace;                     // optional [n_phases + 1] globaltimer stamps of CTA 0 (RQB200_MEGA_TRACE=1)
-};
-
-size_t mega_smem_bytes(int E);
-int launch_ar_mega(const MegaParams& P, int n_sm, cudaStream_t st);
-
 struct ArFast;
 ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, const rqb200_block_weights* body,
                        const rqb200_block_weights* head);
 void ar_fast_destroy(ArFast* f);
 size_t ar_fast_workspace_bytes(const ArFast* f, int B);
-int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B, int start_h, int start_w, float temperature,
-                   const int32_t* top_k, const float* top_p, const float* noise, int64_t noise_stride, float* logits_out,
-                   const int64_t* force, int64_t* out, void* wsp, size_t ws_bytes, cudaStream_t st);
+// positions [idx_begin, idx_end) of the raster; resume != 0: continue on the KV state the previous call left in this workspace
+int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B, int idx_begin, int idx_end, int resume,
+                   float temperature, const int32_t* top_k, const float* top_p, const float* noise, int64_t noise_stride,
+                   float* logits_out, const int64_t* force, int64_t* out, void* wsp, size_t ws_bytes, cudaStream_t st);
+// diagnostics: copies the stage trace of the last replays to the host (RQB200 ar_config.trace); returns the number of launches traced
+int ar_fast_trace(ArFast* f, long long* out_host, int cap_launches, char* names, int names_cap);
 }  // namespace rqb

@@ -246,14 +246,15 @@ int launch_rq_embed(const int64_t* codes, const float* cb, int64_t N, int D, int
     return check_launch("rq_embed");
 }
 
+// form: 0 = pick (the 8x8-register-tile cluster kernel of rq_search2.cu whenever the shape allows: 3.7 vs 7.6 ms at N = 4096,
+// K = 16384; bit-identical results), 1 = this file's 2x4-tile kernel, 2 = rq_search2.cu or fail
 int launch_rq_quantize(const float* x, const float* cb, int64_t N, int K, int C, int D, int64_t* codes, float* quant_list,
-                       float* resid_out, cudaStream_t st) {
+                       float* resid_out, cudaStream_t st, int form) {
     if (C != RQ_C) return fail(RQB200_EINVAL, "rq_quantize: C must be 256");
     if (N < 0 || K <= 0 || D <= 0) return fail(RQB200_EINVAL, "rq_quantize: bad shape");
     if (N == 0) return 0;   // empty input: nothing to do (reference returns empty tensors)
-    // experiment for the next round (csrc/rq_search2.cu): same arithmetic, 8x8 register tile, 2-CTA clusters splitting the codebook
-    if (const char* e = getenv("RQB200_RQ_V2"))
-        if (e[0] == '1' && rq_quantize2_supported(N, K, C)) return launch_rq_quantize2(x, cb, N, K, C, D, codes, quant_list, resid_out, st);
+    if (form != 1 && rq_quantize2_supported(N, K, C)) return launch_rq_quantize2(x, cb, N, K, C, D, codes, quant_list, resid_out, st);
+    if (form == 2) return fail(RQB200_EINVAL, "rq_quantize: shape not supported by the cluster kernel");
     RQB_ENSURE_SMEM(sizeof(RqSmem), rq_quantize_kernel);
     unsigned grid = (unsigned)ceil_div(N, RQ_TN);
     rq_quantize_kernel<<<grid, RQ_THREADS, sizeof(RqSmem), st>>>(x, cb, N, K, D, codes, quant_list, resid_out);
@@ -265,7 +266,11 @@ int launch_rq_quantize(const float* x, const float* cb, int64_t N, int K, int C,
 extern "C" {
 int rqb200_rq_quantize(const float* x, const float* codebook, int64_t N, int K, int C, int D, int64_t* codes,
                        float* quant_list, float* residual_out, void* stream) {
-    return rqb::launch_rq_quantize(x, codebook, N, K, C, D, codes, quant_list, residual_out, (cudaStream_t)stream);
+    return rqb::launch_rq_quantize(x, codebook, N, K, C, D, codes, quant_list, residual_out, (cudaStream_t)stream, 0);
+}
+int rqb200_dbg_rq_quantize(int form, const float* x, const float* codebook, int64_t N, int K, int C, int D, int64_t* codes,
+                           float* quant_list, float* residual_out, void* stream) {
+    return rqb::launch_rq_quantize(x, codebook, N, K, C, D, codes, quant_list, residual_out, (cudaStream_t)stream, form);
 }
 int rqb200_rq_embed_sum(const int64_t* codes, const float* codebook, int64_t N, int D, int K, int C, float* out,
                         void* stream) {

@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("RQB200_LIB", os.path.join(os.path.dirname(_HERE), "cs
 OK, EINVAL, ECUDA, ENODEV, EWORKSPACE, ESTATE = 0, -1, -2, -3, -4, -5
 F32, BF16, F16 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
+AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_NO_NEXT_PREFETCH, AR_LN_CLUSTER = 1, 2, 4, 8, 16, 32, 64, 128
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 c_f32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p
@@ -17,12 +18,13 @@ c_f32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("wqkv", "wproj", "w1", "w2", "bqkv", "bproj", "b1", "b2",
-                                          "ln1_w", "ln1_b", "ln2_w", "ln2_b", "cqkv", "c1")]
+                                          "ln1_w", "ln1_b", "ln2_w", "ln2_b")]
 
 
 class ArConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("embed_dim", "n_head", "n_body", "n_head_layers", "vocab", "H", "W", "D",
-                                         "vocab_cond", "cond_len", "code_dim", "codebook_size", "mode", "weight_dtype")]
+                                         "vocab_cond", "cond_len", "code_dim", "codebook_size", "mode", "weight_dtype",
+                                         "flags", "split_qkv", "split_proj", "split_fc1", "split_fc2")]
 
 
 class ArWeights(C.Structure):
@@ -64,6 +66,8 @@ def lib():
     L.rqb200_rq_embed_depth.argtypes = L.rqb200_rq_embed_sum.argtypes
     L.rqb200_sample_logits.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p,
                                        C.c_void_p]
+    L.rqb200_dbg_rq_quantize.argtypes = [C.c_int] + L.rqb200_rq_quantize.argtypes
+    L.rqb200_dbg_sample_logits.argtypes = [C.c_int] + L.rqb200_sample_logits.argtypes
     L.rqb200_ar_create.restype = C.c_void_p
     L.rqb200_ar_create.argtypes = [C.POINTER(ArConfig), C.POINTER(ArWeights)]
     L.rqb200_ar_destroy.argtypes = [C.c_void_p]
@@ -73,6 +77,10 @@ def lib():
     L.rqb200_ar_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p, C.c_int64, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.rqb200_ar_sample_span.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p, C.c_int64, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.rqb200_ar_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     L.rqb200_ar_last_launches.restype = C.c_int64
     L.rqb200_ar_last_launches.argtypes = [C.c_void_p]
     L.rqb200_vae_create.restype = C.c_void_p
@@ -88,11 +96,9 @@ def lib():
     L.rqb200_vae_last_launches.restype = C.c_int64
     L.rqb200_vae_last_launches.argtypes = [C.c_void_p]
     L.rqb200_dbg_gemm_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.rqb200_dbg_conv_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    L.rqb200_dbg_gemm_gr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.rqb200_dbg_chain.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_float)]
     _lib = L
@@ -101,10 +107,11 @@ def lib():
 
 EXPORTS = ["rqb200_last_error", "rqb200_version", "rqb200_device_count", "rqb200_rq_quantize", "rqb200_rq_embed_sum",
            "rqb200_rq_embed_depth", "rqb200_sample_logits", "rqb200_ar_create", "rqb200_ar_destroy",
-           "rqb200_ar_workspace_bytes", "rqb200_ar_sample", "rqb200_ar_last_launches", "rqb200_vae_create",
+           "rqb200_ar_workspace_bytes", "rqb200_ar_sample", "rqb200_ar_sample_span", "rqb200_ar_trace", "rqb200_ar_last_launches", "rqb200_vae_create",
            "rqb200_vae_destroy", "rqb200_vae_set_tensor", "rqb200_vae_finalize", "rqb200_vae_workspace_bytes",
            "rqb200_vae_decode", "rqb200_vae_decode_code", "rqb200_vae_encode", "rqb200_vae_last_launches",
-           "rqb200_dbg_gemm_tc", "rqb200_dbg_conv_tc", "rqb200_dbg_chain", "rqb200_dbg_gemm_gr"]
+           "rqb200_dbg_gemm_tc", "rqb200_dbg_conv_tc", "rqb200_dbg_chain", "rqb200_dbg_rq_quantize",
+           "rqb200_dbg_sample_logits"]
 
 
 def check(rc, what=""):
@@ -133,8 +140,29 @@ def dtype_code(t):
 
 
 def default_precision():
-    """'exact' (fp32 FFMA, bit-exact-indices gate) or 'fast' (bf16/fp16 tcgen05).  RQB200_PRECISION overrides."""
+    """'exact' (fp32 FFMA, bit-exact-indices gate) or 'fast' (fp16/bf16 tcgen05).  RQB200_PRECISION overrides."""
     return os.environ.get("RQB200_PRECISION", "auto")
+
+
+def fast_dtype():
+    """16-bit operand format of the fast AR tier: fp16 (the reference's autocast class) unless RQB200_FAST_DTYPE=bf16"""
+    return torch.bfloat16 if os.environ.get("RQB200_FAST_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else torch.float16
+
+
+def ar_engine_options():
+    """engine-creation options of the fast AR tier, read ONCE per engine from the environment (diagnostics / experiments)"""
+    env = os.environ.get
+    flags = 0
+    flags |= AR_NO_GRAPH if env("RQB200_NO_GRAPH", "0") == "1" else 0
+    flags |= AR_NO_PDL if env("RQB200_NO_PDL", "0") == "1" else 0
+    flags |= AR_TRACE if env("RQB200_TRACE", "0") == "1" else 0
+    flags |= AR_L2_PREFETCH if env("RQB200_GEMM_L2PF", "0") == "1" else 0
+    flags |= AR_SHALLOW_RING if env("RQB200_GEMM_SHALLOW", "0") == "1" else 0
+    flags |= AR_SEQUENTIAL_PREFILL if env("RQB200_SEQ_PREFILL", "0") == "1" else 0
+    flags |= AR_NO_NEXT_PREFETCH if env("RQB200_NO_NEXT_PF", "0") == "1" else 0
+    flags |= AR_LN_CLUSTER if env("RQB200_LN_CLUSTER", "0") == "1" else 0
+    return {"flags": flags,
+            "splits": [int(env("RQB200_SPLIT_" + k, "0")) for k in ("QKV", "PROJ", "FC1", "FC2")]}
 
 
 def param_fingerprint(module):

@@ -7,8 +7,9 @@ Boundary kept: constructor from an ``RQTransformerConfig`
 ``rqb200_ar_sample`` (csrc/ar_engine.cu): one native call per ``sample``, no per-token host work.
 
 Arithmetic tiers: ``amp=False`` -> 'exact' (fp32 weights/activations, FFMA -- the tier the bit-exact-indices gate is
-defined on); ``amp=True`` -> 'fast' (bf16 weights on tcgen05 tensor cores, fp32 accumulate; the reference's own amp
-path is fp16 autocast).  ``self.precision`` ('exact' | 'fast') or RQB200_PRECISION overrides the ``amp`` mapping."""
+defined on); ``amp=True`` -> 'fast' (fp16 weights / activations / KV on tcgen05 tensor cores, fp32 accumulate -- the
+reference's own amp class is fp16 autocast, transformers.py:114,206; RQB200_FAST_DTYPE=bf16 selects bf16 instead).
+``self.precision`` ('exact' | 'fast') or RQB200_PRECISION overrides the ``amp`` mapping."""
 import ctypes as C
 import os
 from collections import OrderedDict
@@ -54,14 +55,6 @@ class _Stack(_Holder):
         self.blocks = nn.ModuleList([_Block(cfg.block) for _ in range(cfg.n_layer)])
 
 
-def fold_layernorm(W, bias, gamma, beta):
-    """Linear(LayerNorm(x)) = rstd * (W' x - mean * c) + b'  with  W' = W diag(gamma), b' = W beta + bias, c_n = sum_k W'[n, k].
-    c is summed over the bf16-ROUNDED W' (the operand the tensor cores see) so that the mean term cancels exactly.
-    Returns (W' fp32 -- the caller rounds it to bf16 --, b', c)."""
-    Wf = W * gamma[None, :]
-    return Wf, W @ beta + bias, Wf.to(torch.bfloat16).float().sum(1)
-
-
 class RQTransformer(Stage2Model):
     def __init__(self, config):
         super().__init__()
@@ -98,6 +91,7 @@ class RQTransformer(Stage2Model):
             self.cond_classifier = nn.Sequential(OrderedDict([("layer_norm", nn.LayerNorm(E)),
                                                               ("linear", nn.Linear(E, config.vocab_size_cond))]))
         self.precision = None
+        self.noise_budget_bytes = 256 << 20      # bound on the Exp(1) noise buffer sample() draws per span of positions
         self._eng = {}
         self._eng_fp = None
         self._cache = None
@@ -156,7 +150,8 @@ class RQTransformer(Stage2Model):
             return self._eng[key]
         N.require_cuda(self.pos_emb_hw, codebook)
         L = N.lib()
-        wdt = torch.bfloat16 if mode == N.MODE_FAST else torch.float32
+        wdt = N.fast_dtype() if mode == N.MODE_FAST else torch.float32
+        opts = N.ar_engine_options() if mode == N.MODE_FAST else {"flags": 0, "splits": [0, 0, 0, 0]}
         keep = []
 
         def f32(t):
@@ -164,25 +159,10 @@ class RQTransformer(Stage2Model):
             keep.append(t)
             return t.data_ptr()
 
-        tiled = mode == N.MODE_FAST and os.environ.get("RQB200_TILED", "0") == "1"   # measured: no gain (latency-, not DRAM-page-bound)
-
         def wt(t):
             t = t.detach().to(wdt).contiguous()
-            if tiled:
-                # tile-major [N/128][K/64][128][64]: each TMA box of the weight streamer becomes 16 KB of contiguous HBM
-                n, k = t.shape
-                t = t.view(n // 128, 128, k // 64, 64).permute(0, 2, 1, 3).contiguous()
             keep.append(t)
             return t.data_ptr()
-
-        # experiment (fast tier, RQB200_LNFOLD=1, used by the RQB200_GR=1 chain): fold each LayerNorm into the Linear after it,
-        # Linear(LN(x))[n] = rstd*(W'x - mean*c_n) + b'_n with W' = W*diag(gamma), b' = W*beta + b, c_n = sum_k bf16(W')[n,k]
-        lnfold = (mode == N.MODE_FAST and os.environ.get("RQB200_LNFOLD", "0") == "1"
-                  and os.environ.get("RQB200_GR", "0") == "1")
-
-        def folded(W, bias, ln):
-            Wf, d, c = fold_layernorm(W.detach().float(), bias.detach().float(), ln.weight.detach().float(), ln.bias.detach().float())
-            return wt(Wf), f32(d), f32(c)
 
         def blocks(stack):
             arr = (N.BlockWeights * len(stack.blocks))()
@@ -190,12 +170,8 @@ class RQTransformer(Stage2Model):
                 a = b.attn
                 wqkv = torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)
                 bqkv = torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)
-                if lnfold:
-                    arr[i].wqkv, arr[i].bqkv, arr[i].cqkv = folded(wqkv, bqkv, b.ln1)
-                    arr[i].w1, arr[i].b1, arr[i].c1 = folded(b.mlp[0].weight, b.mlp[0].bias, b.ln2)
-                else:
-                    arr[i].wqkv, arr[i].bqkv = wt(wqkv), f32(bqkv)
-                    arr[i].w1, arr[i].b1 = wt(b.mlp[0].weight), f32(b.mlp[0].bias)
+                arr[i].wqkv, arr[i].bqkv = wt(wqkv), f32(bqkv)
+                arr[i].w1, arr[i].b1 = wt(b.mlp[0].weight), f32(b.mlp[0].bias)
                 arr[i].wproj, arr[i].bproj = wt(a.proj.weight), f32(a.proj.bias)
                 arr[i].w2, arr[i].b2 = wt(b.mlp[2].weight), f32(b.mlp[2].bias)
                 arr[i].ln1_w, arr[i].ln1_b = f32(b.ln1.weight), f32(b.ln1.bias)
@@ -209,7 +185,9 @@ class RQTransformer(Stage2Model):
         cfg.vocab, cfg.H, cfg.W, cfg.D = self.vocab_size[0], self.block_size[0], self.block_size[1], self.block_size[2]
         cfg.vocab_cond, cfg.cond_len = self.vocab_size_cond, self.block_size_cond
         cfg.code_dim, cfg.codebook_size = codebook.shape[1], codebook.shape[0]
-        cfg.mode, cfg.weight_dtype = (mode | 0x100) if tiled else mode, N._DT[wdt]
+        cfg.mode, cfg.weight_dtype = mode, N._DT[wdt]
+        cfg.flags = opts["flags"]
+        cfg.split_qkv, cfg.split_proj, cfg.split_fc1, cfg.split_fc2 = opts["splits"]
         if c.head.block.n_head != c.body.block.n_head:
             raise NotImplementedError("rqb200: body and head stacks must share n_head")
         w = N.ArWeights()
@@ -231,7 +209,7 @@ class RQTransformer(Stage2Model):
             return hnd
 
         handle = make()
-        eng = {"handle": handle, "keep": keep, "ws": None, "make": make}
+        eng = {"handle": handle, "keep": keep, "ws": None, "make": make, "dtype": wdt}
         self._eng[key] = eng
         return eng
 
@@ -276,67 +254,78 @@ class RQTransformer(Stage2Model):
         idx0 = start_loc[0] * W + start_loc[1]
         n_tok = max(H * W - idx0, 0) * D
         V = self.vocab_size[0]
-        # the step is latency-bound, not throughput-bound: independent sub-batches on separate streams overlap each other's
-        # kernel latencies (fast tier only; RQB200_AR_STREAMS -- default 1: measured slower at 2 and 4 because the GEMM kernels
-        # own every SM's shared memory)
-        n_streams = 1
-        if mode == N.MODE_FAST and not return_logits and force_codes is None:
-            n_streams = int(os.environ.get("RQB200_AR_STREAMS", "1"))
-            n_streams = max(1, min(n_streams, B // 8 if B >= 8 else 1))
-            if os.environ.get("RQB200_GR", "0") == "1":
-                n_streams = 1        # GT_GR grids spin for their peers: two of them on one GPU could wait for each other forever
+        HWD = H * W * D
         with torch.cuda.device(dev):
-            if noise is None:
-                # one exponential_ per token, in (h,w,d) order: the draws torch.multinomial would make (utils.py:114)
-                noise = torch.empty(n_tok, B, V, dtype=torch.float32, device=dev)
-                for t in range(n_tok):
-                    noise[t].exponential_(1)
-            elif noise is False:
+            draw = noise is None            # draw the Exp(1) noise here, exactly as torch.multinomial would (utils.py:114)
+            if noise is False:
                 noise = None
             logits = torch.empty(n_tok, B, V, dtype=torch.float32, device=dev) if return_logits else None
             out = torch.empty_like(partial)
             kk = (C.c_int32 * D)(*[int(k) for k in ks])
             pp = (C.c_float * D)(*[float(p) for p in ps])
             fc = None if force_codes is None else force_codes.to(torch.int64).contiguous()
-            bounds = [(i * B // n_streams, (i + 1) * B // n_streams) for i in range(n_streams)]
-            if mode == N.MODE_FAST and n_streams == 1 and B > 256:
+            bounds = [(0, B)]
+            if mode == N.MODE_FAST and B > 256:
                 # the tcgen05 tier takes at most 256 batch rows per call (UMMA N <= 256): run equal chunks back to back
                 if return_logits:
                     raise N.NativeError("rqb200: return_logits with B > 256 is not supported on the fast tier")
                 n_chunks = -(-B // 256)
                 bounds = [(i * B // n_chunks, (i + 1) * B // n_chunks) for i in range(n_chunks)]
-            cur = torch.cuda.current_stream(dev)
+            # position spans: when the noise is drawn here it is drawn span by span into one bounded buffer (noise_budget_bytes)
+            # instead of one [n_tok,B,V] tensor (1 GB at 8x8x4, B=64, V=16384); every batch chunk keeps its own engine slot
+            # (workspace + KV state) so that all chunks can resume on the next span
+            n_pos = H * W - idx0
+            per_pos = max(1, D * B * V * 4)
+            span = max(1, min(n_pos, int(self.noise_budget_bytes) // per_pos)) if draw else max(n_pos, 1)
+            if draw and n_tok > 0:
+                noise = torch.empty(min(span, n_pos) * D, B, V, dtype=torch.float32, device=dev)
+            st = torch.cuda.current_stream(dev)
             launches = 0
+            engines = []
             for slot, (lo, hi) in enumerate(bounds):
-                eng = self._engine(codebook, mode, slot if n_streams > 1 else 0)
-                nb = hi - lo
-                need = N.lib().rqb200_ar_workspace_bytes(eng["handle"], nb)
+                eng = self._engine(codebook, mode, slot)
+                need = N.lib().rqb200_ar_workspace_bytes(eng["handle"], hi - lo)
                 if eng["ws"] is None or eng["ws"].numel() < need:
                     eng["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
-                if n_streams > 1:
-                    if "stream" not in eng:
-                        eng["stream"] = torch.cuda.Stream(dev)
-                    st = eng["stream"]
-                    st.wait_stream(cur)
-                else:
-                    st = cur
+                engines.append(eng)
 
-                def off(t, row_elems, esize):
-                    return C.c_void_p(t.data_ptr() + lo * row_elems * esize) if t is not None else C.c_void_p(0)
+            def off(t, lo, row_elems, esize, extra=0):
+                return C.c_void_p(t.data_ptr() + (lo * row_elems + extra) * esize) if t is not None else C.c_void_p(0)
 
-                HWD = H * W * D
-                N.check(N.lib().rqb200_ar_sample(
-                    eng["handle"], off(partial, HWD, 8), off(cond_t, self.block_size_cond, 8), nb, int(start_loc[0]),
-                    int(start_loc[1]), float(temperature), kk, pp, off(noise, V, 4), 0 if noise is None else B * V,
-                    off(logits, V, 4), off(fc, HWD, 8), off(out, HWD, 8), N.ptr(eng["ws"]), eng["ws"].numel(),
-                    C.c_void_p(st.cuda_stream)), "ar_sample")
-                launches += N.lib().rqb200_ar_last_launches(eng["handle"])
-            if n_streams > 1:
-                for slot in range(n_streams):
-                    cur.wait_stream(self._engine(codebook, mode, slot)["stream"])
+            for p0 in range(idx0, H * W, span):
+                p1 = min(p0 + span, H * W)
+                if draw:
+                    # one exponential_ per token, in (h,w,d) order: the draws torch.multinomial would make
+                    for t in range((p1 - p0) * D):
+                        noise[t].exponential_(1)
+                tok0 = 0 if draw else (p0 - idx0) * D                  # first token of this span inside `noise`
+                for eng, (lo, hi) in zip(engines, bounds):
+                    N.check(N.lib().rqb200_ar_sample_span(
+                        eng["handle"], off(partial, lo, HWD, 8), off(cond_t, lo, self.block_size_cond, 8), hi - lo, p0, p1,
+                        int(p0 > idx0), float(temperature), kk, pp, off(noise, lo, V, 4, tok0 * B * V),
+                        0 if noise is None else B * V, off(logits, lo, V, 4, (p0 - idx0) * D * B * V), off(fc, lo, HWD, 8),
+                        off(out, lo, HWD, 8), N.ptr(eng["ws"]), eng["ws"].numel(), C.c_void_p(st.cuda_stream)), "ar_sample")
+                    launches += N.lib().rqb200_ar_last_launches(eng["handle"])
+            if n_tok == 0:
+                out.copy_(partial)
         self.last_launches = launches
         N.launch_count["total"] += launches
         return (out, logits) if return_logits else out
+
+    def native_trace(self):
+        """diagnostics (RQB200_TRACE=1, fast tier): [(name, t_entry, t_dependency_resolved, t_mid, t_done)] in ns for every launch
+        slot of the last replay of each captured graph -- where the time of one AR position goes"""
+        rows = []
+        for key, eng in self._eng.items():
+            cap = 4096
+            buf = (C.c_longlong * (4 * cap))()
+            names = C.create_string_buffer(cap * 16)
+            n = N.lib().rqb200_ar_trace(eng["handle"], buf, cap, names, len(names))
+            nm = names.value.decode().split("\n")
+            for i in range(max(n, 0)):
+                if buf[4 * i]:
+                    rows.append((nm[i] if i < len(nm) else "?", buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3], i))
+        return rows
 
     @torch.no_grad()
     def sample(self, partial_sample, model_aux=None, cond=None, start_loc=(0, 0), temperature=1.0, top_k=None, top_p=None,

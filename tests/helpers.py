@@ -26,13 +26,28 @@ def vae_config(name):
     return augment_arch_defaults(cfg)
 
 
+_AR_CACHE = {}
+
+
 def build_ar(name, layouts, seed, device="cuda"):
+    """synthetic-weight transformer; the large shapes are memoised per test session (regenerating 3.9 B seeded weights on the CPU
+    takes minutes) -- tests set model.precision / the engine options they need explicitly"""
+    key = (name, seed, str(device))
+    if key in _AR_CACHE:
+        model, sd = _AR_CACHE[key]
+        model._invalidate_native()
+        model.precision = None
+        model.noise_budget_bytes = 256 << 20
+        return model, sd
     with torch.device("meta"):
         model, _ = create_model(ar_config(name))
     sd = synth.synth_state_dict(layouts["ar/" + name], seed)
     model = model.to_empty(device=device)
     model.load_state_dict({k: v.to(device) for k, v in sd.items()})
-    return model.eval(), sd
+    model = model.eval()
+    if AR_ZOO[name][0] >= 1024:
+        _AR_CACHE[key] = (model, sd)
+    return model, sd
 
 
 def build_vae(name, layouts, seed, device="cuda"):

@@ -1,7 +1,9 @@
-"""Fast tier (bf16 tcgen05, PDL chain, CUDA graphs) of the AR step against the fp32 exact tier, which is itself pinned
-bit-exactly to the reference fixtures (tests/test_gpu_parity.py).  Protocol: teacher-forced step parity
--- logits within a bf16 error bound, indices identical except where the fp32 tier's own decision margin is inside that
-bound -- plus self-consistency of the free-running loop (graph == no graph, run-to-run determinism, resume)."""
+"""Fast tier (fp16 -- the reference's autocast class -- or bf16 operands on tcgen05, PDL chain, CUDA graphs) of the AR step
+against (a) the logits the unmodified reference stored in tests/golden/ar.pt and (b) the fp32 exact tier, which is itself
+pinned bit-exactly to the reference fixtures (tests/test_gpu_parity.py).  Protocol:
+teacher-forced step parity -- logits within a 16-bit error bound, indices identical except where the fp32 decision margin is
+inside that bound --, the free-running first-divergence statistic against the reference's own trajectories, and
+self-consistency of the free-running loop (graph == no graph, run-to-run determinism, resume, chunked noise)."""
 import os
 
 import pytest
@@ -17,7 +19,7 @@ DEV = "cuda"
 
 
 def _case(name, golden, layouts):
-    g = golden("ar")["ar"][name]
+    g = golden("ar2" if name in ("cc3m654m", "cc3m654m_16", "t2i3900m") else "ar")["ar"][name]
     E, nh, nb_, nhl, V, bs, vc, cl = AR_ZOO[name]
     model, sd = build_ar(name, layouts, g["weight_seed"])
     cb = synth.randn_seeded((V, 256), g["codebook_seed"]).to(DEV)
@@ -25,10 +27,21 @@ def _case(name, golden, layouts):
     return g, model, CodebookAux(cb), cond, bs, V
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_txt", "ffhq355m", "in1400m"])
-def test_fast_tier_teacher_forced_step_parity(golden, layouts, name):
-    g, model, aux, cond, bs, V = _case(name, golden, layouts)
-    codes = g["runs"][-1]["codes"].long().to(DEV)          # a seeded top-k trajectory of the reference
+def _with_env(model, env, fn):
+    for k, v in env.items():
+        os.environ[k] = v
+    model._invalidate_native()
+    try:
+        return fn()
+    finally:
+        for k in env:
+            del os.environ[k]
+        model._invalidate_native()
+
+
+def fast_tier_parity_stats(model, aux, cond, g, bs, V):
+    """the numbers the bench line's `parity` record carries: teacher-forced on the reference's last (seeded top-k) trajectory"""
+    codes = g["runs"][-1]["codes"].long().to(DEV)
     tf = dict(noise=False, return_logits=True, force_codes=codes)
     model.precision = "exact"
     _, lg32 = model._native_sample(codes, aux, cond, (0, 0), 1.0, None, None, False, **tf)
@@ -36,17 +49,53 @@ def test_fast_tier_teacher_forced_step_parity(golden, layouts, name):
     out, lg16 = model._native_sample(codes, aux, cond, (0, 0), 1.0, None, None, True, **tf)
     assert torch.equal(out, codes)
     err = (lg16 - lg32).abs()
-    std = float(lg32.std())
-    rms = float(err.pow(2).mean().sqrt())
-    print("%s: logits std %.3f, bf16-tier error rms %.4f max %.4f" % (name, std, rms, float(err.max())))
-    assert rms < 0.02 * std and float(err.max()) < 0.15 * std        # bf16 weights+activations, fp32 accumulate
-    # greedy index parity with margin audit
     top2 = lg32.topk(2, dim=-1).values
     margin = top2[..., 0] - top2[..., 1]
     differ = lg16.argmax(-1) != lg32.argmax(-1)
-    bound = 2 * err.amax(-1)
-    assert not bool((differ & (margin > bound)).any()), "index flip outside the arithmetic error bound"
-    print("%s: %d / %d greedy indices differ, all inside the margin bound" % (name, int(differ.sum()), differ.numel()))
+    outside = differ & (margin > 2 * err.amax(-1))
+    return dict(std=float(lg32.std()), rms=float(err.pow(2).mean().sqrt()), max=float(err.max()), flips=int(differ.sum()),
+                flips_outside_margin=int(outside.sum()), n=differ.numel(), lg16=lg16, lg32=lg32)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_txt", "ffhq355m", "in1400m", "cc3m654m", "t2i3900m"])
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+def test_fast_tier_teacher_forced_step_parity(golden, layouts, name, fmt):
+    g, model, aux, cond, bs, V = _case(name, golden, layouts)
+    r = _with_env(model, {"RQB200_FAST_DTYPE": fmt}, lambda: fast_tier_parity_stats(model, aux, cond, g, bs, V))
+    print("%s %s: logits std %.3f, fast-tier error rms %.5f max %.5f; %d / %d greedy indices differ, %d outside the margin bound"
+          % (name, fmt, r["std"], r["rms"], r["max"], r["flips"], r["n"], r["flips_outside_margin"]))
+    # fp16 has three more mantissa bits than bf16: its bound is 4x tighter
+    k = 1.0 if fmt == "bf16" else 0.25
+    assert r["rms"] < 0.02 * k * r["std"] and r["max"] < 0.15 * k * r["std"]
+    assert r["flips_outside_margin"] == 0, "index flip outside the arithmetic error bound"
+    # ... and against the logits the REFERENCE itself stored for this trajectory (golden fixture), not only our exact tier
+    run = g["runs"][-1]
+    if run["logits"]:
+        for step, lg in run["logits"].items():
+            e = (r["lg16"][step].cpu() - lg).abs()
+            assert float(e.max()) < 0.15 * k * r["std"] + 2e-4, (step, float(e.max()))
+
+
+@pytest.mark.parametrize("name", ["ffhq355m", "in1400m"])
+def test_fast_tier_free_running_first_divergence_vs_reference(golden, layouts, name):
+    """SURVEY Appendix E statistic: free-running fp16 sampling against the reference's own fp32 trajectories under the same
+    injected noise -- a 16-bit tier cannot pass a bit-exact free-running gate (the reference itself does not: bf16-vs-fp32 of the
+    SAME code diverges at step 48-120 greedy); what is recorded is the first divergent step per sample.  Gate: no divergence
+    before step 8 for seeded top-k (wide Exp(1) margins), and every sample's prefix up to its divergence is identical."""
+    g, model, aux, cond, bs, V = _case(name, golden, layouts)
+    model.precision = "fast"
+    B = g["B"]
+    n_tok = bs[0] * bs[1] * bs[2]
+    for run in g["runs"]:
+        st = run["setting"]
+        noise = noise_tensor(run["noise_seed"], n_tok, B, V)
+        codes = model._native_sample(torch.zeros(B, *bs, dtype=torch.long, device=DEV), aux, cond, (0, 0), 1.0, st.get("top_k"),
+                                     st.get("top_p"), True, noise=noise).cpu().reshape(B, -1)
+        ref = run["codes"].long().reshape(B, -1)
+        first = [int((codes[b] != ref[b]).nonzero()[0]) if bool((codes[b] != ref[b]).any()) else n_tok for b in range(B)]
+        print("%s %s: first divergent step per sample %s of %d" % (name, st, first, n_tok))
+        if st.get("top_k", 0) and st.get("top_k") > 1:
+            assert min(first) >= 8, first
 
 
 def test_fast_tier_free_running_consistency(golden, layouts):
@@ -69,30 +118,41 @@ def test_fast_tier_free_running_consistency(golden, layouts):
     # resume from the middle reproduces the tail when fed the same noise tail
     h0, w0 = bs[0] // 2, 1
     skip = (h0 * bs[1] + w0) * bs[2]
-    c = model._native_sample(a, aux, cond, (h0, w0), 1.0, 100, 0.95, True, noise=noise[skip:].contiguous())
+    c = _with_env(model, {"RQB200_SEQ_PREFILL": "1"},
+                  lambda: model._native_sample(a, aux, cond, (h0, w0), 1.0, 100, 0.95, True, noise=noise[skip:].contiguous()))
     assert torch.equal(c, a)
-    # CUDA graphs and PDL are pure scheduling: same codes without them (persistent form and per-op chain alike)
-    for mega in ("1", "0"):
-        os.environ["RQB200_MEGA"] = mega
-        model._invalidate_native()
-        base = model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=noise)
-        for var in ("RQB200_NO_GRAPH", "RQB200_NO_PDL"):
-            os.environ[var] = "1"
-            try:
-                model._invalidate_native()
-                d = model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=noise)
-            finally:
-                del os.environ[var]
-                model._invalidate_native()
-            assert torch.equal(base, d), (var, mega)
-    # persistent form vs per-op chain: same arithmetic up to the LayerNorm reduction order
-    _, lg_chain = model._native_sample(a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a)
-    os.environ["RQB200_MEGA"] = "1"
-    model._invalidate_native()
-    _, lg_mega = model._native_sample(a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a)
-    del os.environ["RQB200_MEGA"]
-    model._invalidate_native()
-    assert float((lg_chain - lg_mega).abs().max()) < 2e-2 * float(lg_mega.std())
+    # the default (batched, one M = B*T pass) prefill sums in a different order: same prefix by construction, and on this toy the
+    # same tail unless a sampled token sat on a rounding-level tie
+    cb = model._native_sample(a, aux, cond, (h0, w0), 1.0, 100, 0.95, True, noise=noise[skip:].contiguous())
+    assert torch.equal(cb.flatten(1)[:, :skip], a.flatten(1)[:, :skip])
+    print("resume with batched prefill: %d of %d tail codes differ from the sequential-prefill trajectory"
+          % (int((cb != a).sum()), cb.numel() - B * skip))
+    # CUDA graphs, PDL, ring depth and L2 prefetch are pure scheduling: same codes without / with them
+    for var in ("RQB200_NO_GRAPH", "RQB200_NO_PDL", "RQB200_GEMM_SHALLOW", "RQB200_GEMM_L2PF", "RQB200_TRACE"):
+        d = _with_env(model, {var: "1"}, lambda: model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=noise))
+        assert torch.equal(a, d), var
+    # 2-CTA-cluster LayerNorm rows: the same statistics up to the order of one fp32 combination
+    _, lg_a = model._native_sample(a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a)
+    _, lg_c = _with_env(model, {"RQB200_LN_CLUSTER": "1"}, lambda: model._native_sample(
+        a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a))
+    assert float((lg_a - lg_c).abs().max()) < 2e-3 * float(lg_a.std())
+    # noise drawn span by span (bounded buffer, KV state resumed between spans) == one call with the whole noise tensor
+    torch.manual_seed(4321)
+    full = torch.empty(n_tok, B, V, device=DEV)
+    for t in range(n_tok):
+        full[t].exponential_(1)
+    want = model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=full)
+    for budget in (1, 3 * 4 * B * V * 4, 1 << 40):            # one position per span, three, everything
+        model.noise_budget_bytes = budget
+        torch.manual_seed(4321)
+        got = model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True)
+        assert torch.equal(got, want), budget
+    model.precision = "exact"                                 # the exact tier resumes between spans the same way
+    want32 = model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, False, noise=full)
+    model.noise_budget_bytes = 2 * 4 * B * V * 4
+    torch.manual_seed(4321)
+    assert torch.equal(model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, False), want32)
+    model.noise_budget_bytes = 256 << 20
 
 
 def test_fast_tier_text_conditioned_prefill(golden, layouts):
@@ -108,32 +168,24 @@ def test_fast_tier_text_conditioned_prefill(golden, layouts):
     _, lg32 = model._native_sample(a, aux, cond, (0, 0), 1.0, None, None, False, noise=False, return_logits=True, force_codes=a)
     model.precision = "fast"
     _, lg16 = model._native_sample(a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a)
-    assert float((lg16 - lg32).abs().max()) < 0.15 * float(lg32.std())
-
-
-def test_fast_tier_cc3m_654m_text_conditioned_step_parity(layouts):
-    """BASELINE config 4 shape (CC-3M 654M: E=1280, 20 heads, 26+4 layers, 32 text tokens of prefix): fast tier vs exact tier,
-    teacher-forced on a random trajectory"""
-    from tests.helpers import build_ar
-    E, nh, nb_, nhl, V, bs, vc, cl = AR_ZOO["cc3m654m"]
-    model, sd = build_ar("cc3m654m", layouts, 31)
-    cb = synth.randn_seeded((V, 256), 32).to(DEV)
-    aux = CodebookAux(cb)
-    B = 2
-    cond = synth.randint_seeded(0, vc, (B, cl), 33).to(DEV)
-    codes = synth.randint_seeded(0, V, (B, *bs), 34).to(DEV)
-    tf = dict(noise=False, return_logits=True, force_codes=codes)
-    model.precision = "exact"
-    _, lg32 = model._native_sample(codes, aux, cond, (0, 0), 1.0, None, None, False, **tf)
-    model.precision = "fast"
-    _, lg16 = model._native_sample(codes, aux, cond, (0, 0), 1.0, None, None, True, **tf)
-    err = (lg16 - lg32).abs()
-    std = float(lg32.std())
-    print("cc3m654m: logits std %.3f, bf16-tier error rms %.4f max %.4f" % (std, float(err.pow(2).mean().sqrt()), float(err.max())))
-    assert float(err.pow(2).mean().sqrt()) < 0.02 * std and float(err.max()) < 0.15 * std
-    top2 = lg32.topk(2, dim=-1).values
-    differ = lg16.argmax(-1) != lg32.argmax(-1)
-    assert not bool((differ & ((top2[..., 0] - top2[..., 1]) > 2 * err.amax(-1))).any())
+    assert float((lg16 - lg32).abs().max()) < 0.15 * 0.25 * float(lg32.std())
+    # batched prefill (one M = B*T pass) against the token-by-token prefill (its oracle): same logits up to summation order
+    _, lgseq = _with_env(model, {"RQB200_SEQ_PREFILL": "1"}, lambda: model._native_sample(
+        a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a))
+    d = float((lg16 - lgseq).abs().max())
+    print("batched vs sequential prefill (cond_len 4): max logit difference %.2e" % d)
+    assert d < 0.02 * float(lg32.std())
+    # start_loc resume: prefix = 4 cond tokens + the code tokens of 5 positions, batched vs sequential
+    h0, w0 = 1, 2
+    skip = (h0 * bs[1] + w0) * bs[2]
+    rb = model._native_sample(a, aux, cond, (h0, w0), 1.0, 64, None, True, noise=noise[skip:].contiguous(), return_logits=True)
+    rs = _with_env(model, {"RQB200_SEQ_PREFILL": "1"}, lambda: model._native_sample(
+        a, aux, cond, (h0, w0), 1.0, 64, None, True, noise=noise[skip:].contiguous(), return_logits=True))
+    assert torch.equal(rs[0], a), "sequential-prefill resume must reproduce the trajectory bit for bit"
+    d = float((rb[1][0] - rs[1][0]).abs().max())
+    print("resume at (%d,%d): batched vs sequential prefill, first-step max logit difference %.2e" % (h0, w0, d))
+    assert d < 0.02 * float(lg32.std())
+    assert torch.equal(rb[0].flatten(1)[:, :skip], a.flatten(1)[:, :skip])
 
 
 def test_16x16_grid_with_text_prefix_exact_tier_vs_oracle():
@@ -166,7 +218,7 @@ def test_16x16_grid_with_text_prefix_exact_tier_vs_oracle():
     fast = model._native_sample(torch.zeros(B, *bs, dtype=torch.long, device=DEV), CodebookAux(cb.to(DEV)), cond.to(DEV), (0, 0), 1.0, 50,
                                 0.9, True, noise=noise_tensor(43, n_tok, B, V))
     assert fast.shape == ref.shape and int(fast.min()) >= 0 and int(fast.max()) < V
-    # bf16 tier: the first tokens (no accumulated feedback yet) agree with the fp32 trajectory
+    # fp16 tier: the first tokens (no accumulated feedback yet) agree with the fp32 trajectory
     assert torch.equal(fast.cpu().flatten(1)[:, :8], ref.flatten(1)[:, :8])
 
 

@@ -130,35 +130,3 @@ def test_no_cpu_fallback():
     with pytest.raises(N.NativeError):
         vae.quantizer.quantize(torch.zeros(1, 4, 4, 256))
     assert N.lib().rqb200_device_count() == 0
-
-
-def test_layernorm_fold_identity():
-    """host half of the RQB200_LNFOLD experiment: the folded form equals Linear(LayerNorm(x)) (fp64: exactly; with bf16 operands:
-    to the same error as the unfolded bf16 path for rows whose mean is small against their spread)"""
-    import torch
-    from rqvae.models.rqtransformer.transformers import fold_layernorm
-    torch.manual_seed(0)
-    E, n, B = 256, 384, 16
-    W, b = torch.randn(n, E, dtype=torch.float64) * 0.05, torch.randn(n, dtype=torch.float64) * 0.1
-    g, be = 1 + 0.1 * torch.randn(E, dtype=torch.float64), 0.1 * torch.randn(E, dtype=torch.float64)
-    x = torch.randn(B, E, dtype=torch.float64) * 1.3 + 0.2
-    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (E,), g, be, 1e-5), W, b)
-    Wf, d, _ = fold_layernorm(W, b, g, be)
-    c = Wf.sum(1)                                          # exact column sums for the fp64 identity
-    mean = x.mean(-1, keepdim=True)
-    rstd = torch.rsqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
-    out = rstd * (x @ Wf.T - mean * c[None, :]) + d
-    assert float((out - ref).abs().max()) < 1e-10
-    # bf16 operands, tile statistics combined as the kernels do (Chan)
-    Wf32, d32, c32 = fold_layernorm(W.float(), b.float(), g.float(), be.float())
-    x32 = x.float()
-    xt = x32.view(B, E // 128, 128)
-    s1, m2 = xt.sum(-1), ((xt - xt.mean(-1, keepdim=True)) ** 2).sum(-1)
-    mu = s1.sum(-1) / E
-    rs = torch.rsqrt((m2 + 128 * (s1 / 128 - mu[:, None]) ** 2).sum(-1) / E + 1e-5)
-    bf = lambda t: t.to(torch.bfloat16).float()  # noqa: E731
-    fold = rs[:, None] * (bf(x32) @ bf(Wf32).T - mu[:, None] * c32[None, :]) + d32
-    base = bf(torch.nn.functional.layer_norm(x32, (E,), g.float(), be.float(), 1e-5)) @ bf(W.float()).T + b.float()
-    e_fold = float((fold.double() - ref).norm() / ref.norm())
-    e_base = float((base.double() - ref).norm() / ref.norm())
-    assert e_fold < 1.5 * e_base + 1e-4, (e_fold, e_base)

@@ -46,6 +46,7 @@ extern "C" {
 #define RQB200_AR_SHALLOW_RING 16       /* half-depth GEMM rings: two GEMM CTAs of consecutive launches share an SM        */
 #define RQB200_AR_SEQUENTIAL_PREFILL 32 /* prefill the prefix token by token with the single-step graph (the prefill oracle) */
 #define RQB200_AR_NO_NEXT_PREFETCH 64   /* fc1 does not pull fc2's weights into L2                                          */
+#define RQB200_AR_NO_KV_PREFETCH 256    /* attention does not pull the next layer's cache rows into L2 ahead of time          */
 #define RQB200_AR_LN_CLUSTER 128        /* reduction + LayerNorm rows split over 2-CTA clusters (DSMEM statistics exchange)  */
 
 const char* rqb200_last_error(void);
@@ -104,6 +105,9 @@ typedef struct rqb200_ar_weights {
     const float* codebook;                                /* [K,C] f32 (model_aux.get_code_emb_with_depth)       */
     const rqb200_block_weights* body;                     /* host array [n_body]                                 */
     const rqb200_block_weights* head;                     /* host array [n_head_layers]                          */
+    /* optional (cond_len > 1): cond_classifier (transformers.py:100-104) -- only rqb200_ar_forward's cond_logits use it */
+    const void* w_ccls;                                   /* [Vc,E], Vc = vocab_cond rounded up to 128 (zero rows); weight dtype; NULL when absent */
+    const float *b_ccls, *ccls_ln_w, *ccls_ln_b;
 } rqb200_ar_weights;
 
 typedef struct rqb200_ar rqb200_ar;
@@ -134,6 +138,14 @@ int rqb200_ar_sample_span(rqb200_ar* h, const int64_t* partial, const int64_t* c
                           float temperature, const int32_t* top_k_host, const float* top_p_host, const float* noise,
                           int64_t noise_stride, float* logits_out, const int64_t* force_codes, int64_t* out_codes,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* RQTransformer.forward (transformers.py:113-188): teacher-forced logits of complete code maps, all positions at once (fast tier:
+ * M = B*T row GEMMs on tcgen05 + causal attention; exact tier: returns RQB200_EINVAL -- use rqb200_ar_sample with force_codes and
+ * logits_out, the sequential replay).  codes [B,H,W,D] int64, cond [B,cond_len] or NULL.
+ * logits_out [D][H*W][B][V] f32 (token-major: logits of (b, pos, d) at ((d*H*W + pos)*B + b)*V); cond_logits_out (nullable,
+ * cond_len > 1 and w_ccls given) [cond_len-1][B][Vc] f32 with Vc = vocab_cond rounded up to a multiple of 128. */
+size_t rqb200_ar_forward_workspace_bytes(const rqb200_ar* h, int B);
+int rqb200_ar_forward(rqb200_ar* h, const int64_t* codes, const int64_t* cond, int B, float* logits_out, float* cond_logits_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* fast tier with RQB200_AR_TRACE: copies 4 globaltimer stamps (ns: entry, dependency resolved, accumulator ready / mid, done) per
  * launch slot of the last graph replays to out_host[cap_launches][4] and the slot names ('\n'-separated) to names; returns the
  * number of slots (0 when tracing is off).  Synchronises the device. */

@@ -255,8 +255,9 @@ def ar_sample(sd, cfg, partial_sample, codebook, cond=None, start_loc=(0, 0), te
     return xs
 
 
-def ar_forward(sd, cfg, xs, codebook, cond=None):
-    """transformers.py:113-188 -- teacher-forced logits [B,H,W,D,V] (cond_len==1 return convention)."""
+def ar_forward(sd, cfg, xs, codebook, cond=None, with_cond_logits=False):
+    """transformers.py:113-188 -- teacher-forced logits [B,H,W,D,V]; with_cond_logits (cond_len > 1): also the cond_classifier
+    logits of latents[:, :cond_len-1] (:153-156), the reference's two-value return convention (:185-186)."""
     B, H, W, D = xs.shape
     xs = xs.reshape(B, H * W, D)
     cond = torch.zeros(B, cfg.cond_len, dtype=torch.long) if cond is None else cond.reshape(B, cfg.cond_len)
@@ -269,7 +270,10 @@ def ar_forward(sd, cfg, xs, codebook, cond=None):
     dctx = _linear(sd, "head_mlp", torch.cumsum(embed_code_with_depth(xs, codebook), dim=-2))
     full = torch.cat([sp.view(B, L, 1, -1), dctx[:, :, :-1, :]], dim=-2).reshape(B * L, D, -1) + sd["pos_emb_d"][:, :D, :]
     out = stack(sd, "head_transformer", full, cfg.n_headl, cfg.nh).reshape(B, H, W, D, -1)
-    return _linear(sd, "classifier.linear", _layer_norm(sd, "classifier.layer_norm", out))
+    logits = _linear(sd, "classifier.linear", _layer_norm(sd, "classifier.layer_norm", out))
+    if with_cond_logits and cl > 1:
+        return logits, _linear(sd, "cond_classifier.linear", _layer_norm(sd, "cond_classifier.layer_norm", lat[:, :cl - 1]))
+    return logits
 
 
 # ------------------------------------------------------------------------------------------------ P2

@@ -198,6 +198,20 @@ int rqb200_ar_sample(rqb200_ar* h, const int64_t* partial, const int64_t* cond, 
     return rqb200_ar_sample_span(h, partial, cond, B, std::min(start_h * h->cfg.W + start_w, HW), HW, 0, temperature, top_k_host,
                                  top_p_host, noise, noise_stride, logits_out, force_codes, out_codes, workspace, workspace_bytes, stream);
 }
+size_t rqb200_ar_forward_workspace_bytes(const rqb200_ar* h, int B) {
+    if (!h || !h->fast || B <= 0) return 0;
+    return rqb::ar_fast_forward_workspace_bytes(h->fast, B);
+}
+int rqb200_ar_forward(rqb200_ar* h, const int64_t* codes, const int64_t* cond, int B, float* logits_out, float* cond_logits_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !codes || !logits_out || !workspace) return rqb::fail(RQB200_EINVAL, "ar_forward: null argument");
+    if (rqb200_device_count() <= 0) return rqb::fail(RQB200_ENODEV, "ar_forward: no CUDA device");
+    if (!h->fast) return rqb::fail(RQB200_EINVAL, "ar_forward: the batched forward is a fast-tier path (exact tier: teacher-forced rqb200_ar_sample)");
+    rqb::g_launches = 0;
+    int rc = rqb::ar_fast_forward(h->fast, codes, cond, B, logits_out, cond_logits_out, workspace, workspace_bytes, (cudaStream_t)stream);
+    h->last_launches = rqb::g_launches;
+    return rc;
+}
 int rqb200_ar_trace(rqb200_ar* h, long long* out_host, int cap_launches, char* names, int names_cap) {
     if (!h || !h->fast || !out_host) return 0;
     cudaDeviceSynchronize();

@@ -247,38 +247,57 @@ act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restr
 }
 
 // one warp per (b, head): reduce the split-K qkv partials (+bias), append k,v at row t of the 16-bit cache, attend.
-// lane <-> dims (2*lane, 2*lane+1) for q/k/v/out; lane <-> key for the scores (q and the probabilities are
-// broadcast through shared memory).  T <= 512.
-// The cached rows [0, t) were written by EARLIER graph replays, so they do not depend on the upstream kernel of the chain:
-// with early_t the warp pulls them into L2 before griddepcontrol.wait (the step reads ~0.5 GB of KV per position -- more than
-// L2 holds across a position -- so they would otherwise come from HBM behind two dependent round trips), and after the wait
-// every K row of a 64-key pass / every V row of a 64-row pass is in flight at once.
+// lane <-> dims (2*lane, 2*lane+1) for q/k/v/out everywhere: every cache row is read as ONE coalesced 128 B line per warp
+// instruction (a lane-per-key row read costs 8x the L1 wavefronts); the per-key dot products are finished with a 31-shuffle
+// transpose-reduce per 32 keys, after which lane j holds the score of key j.  T <= 512.
+// The cached rows [0, t) were written by EARLIER graph replays, so they do not depend on the upstream kernel of the chain.  At
+// T = 64, B = 64 one layer's rows are 25 MB -- 3.9 us of HBM time that used to sit behind two dependent round trips.  With
+// early_t the warp pulls rows into L2 BEFORE griddepcontrol.wait: the NEXT layer's rows (kc_pf / vc_pf: a whole block of lead
+// time) and, when pf_self is set (first layer of a stack), its own.  After the wait up to 64 K rows / 64 V rows are in flight.
 constexpr int AF_MAXT = 512;
+
+__device__ __forceinline__ void af_prefetch_rows(const h16* base, int t, int lane) {
+    for (int j = lane; j < t; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)j * 64));
+}
+// pv[u] = this lane's partial dot product for key u (u < 32); returns the full dot product of key `lane`
+__device__ __forceinline__ float af_transpose_reduce(float (&pv)[32], int lane) {
+#pragma unroll
+    for (int S = 16; S >= 1; S >>= 1) {
+        const bool up = (lane & S) != 0;
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            const float send = up ? pv[i] : pv[i + S];
+            const float keep = up ? pv[i + S] : pv[i];
+            pv[i] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+        }
+    }
+    return pv[0];
+}
+
 __global__ void __launch_bounds__(128)
 attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, h16* __restrict__ kc, h16* __restrict__ vc,
                  h16* __restrict__ att, int B, int E, int nh, int Tmax, const int* __restrict__ t_ptr, int t_host, int early_t,
-                 int bf, long long* tr) {
-    extern __shared__ float af_smem[];              // qs[4][64] | ps[4][tp]
+                 const h16* __restrict__ kc_pf, const h16* __restrict__ vc_pf, int pf_self, int bf, long long* tr) {
+    extern __shared__ float af_smem[];              // ps[4][tp]
     const int tp = (Tmax + 31) & ~31;
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    float* qs = af_smem + wq * 64;
-    float* ps = af_smem + 4 * 64 + wq * tp;
+    float* ps = af_smem + wq * tp;
     tc::pdl_launch_dependents();
     TR_IN(tr);
     const int bh = blockIdx.x * 4 + wq;
     const bool valid = bh < B * nh;
     const int b = valid ? bh / nh : 0, h = valid ? bh % nh : 0;
-    h16* kb = kc + ((int64_t)(b * nh + h) * Tmax) * 64;
-    h16* vb = vc + ((int64_t)(b * nh + h) * Tmax) * 64;
+    const int64_t pair = ((int64_t)(b * nh + h) * Tmax) * 64;
+    h16* kb = kc + pair;
+    h16* vb = vc + pair;
     int t = 0;
     if (early_t) {
         // (position counters are only advanced by the LAST kernel of a graph; no kernel upstream of this one in the graph writes them)
         t = t_ptr ? *reinterpret_cast<const volatile int*>(t_ptr) : t_host;
-        if (valid)
-            for (int j = lane; j < t; j += 32) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (int64_t)j * 64));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (int64_t)j * 64));
-            }
+        if (valid) {
+            if (pf_self) { af_prefetch_rows(kb, t, lane); af_prefetch_rows(vb, t, lane); }
+            if (kc_pf) { af_prefetch_rows(kc_pf + pair, t, lane); af_prefetch_rows(vc_pf + pair, t, lane); }
+        }
     }
     tc::pdl_wait();
     TR_DEP(tr);
@@ -301,55 +320,29 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     *reinterpret_cast<uint32_t*>(vb + (int64_t)t * 64 + 2 * lane) = v2;
     // use the 16-bit-rounded q/k/v everywhere (what a later step reads back from the cache)
     const float2 qf = unpack_h16x2(pack_h16x2(q.x, q.y, bf), bf), kf = unpack_h16x2(k2, bf), vf = unpack_h16x2(v2, bf);
-    qs[2 * lane] = qf.x;
-    qs[2 * lane + 1] = qf.y;
-    __syncwarp();
     const float s_new = warp_sum(qf.x * kf.x + qf.y * kf.y) * 0.125f;
     float m = s_new;
-    for (int j0 = 0; j0 < t; j0 += 64) {          // scores of the cached rows: two rows per lane, 16 x 16 B in flight
-        const int ja = j0 + lane, jb = j0 + 32 + lane;
-        uint4 wa[8], wb[8];
-        if (ja < t) {
-            const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)ja * 64);
+    for (int j0 = 0; j0 < t; j0 += 64) {          // scores of the cached rows: 64 coalesced row reads in flight
+        uint32_t kr[64];
 #pragma unroll
-            for (int u = 0; u < 8; u++) wa[u] = kr[u];
-        }
-        if (jb < t) {
-            const uint4* kr = reinterpret_cast<const uint4*>(kb + (int64_t)jb * 64);
+        for (int u = 0; u < 64; u++)
+            kr[u] = (j0 + u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)(j0 + u) * 64 + 2 * lane) : 0u;
 #pragma unroll
-            for (int u = 0; u < 8; u++) wb[u] = kr[u];
-        }
-        if (ja < t) {
-            float acc = 0.f;
+        for (int half = 0; half < 2; half++) {
+            if (j0 + half * 32 < t) {                                  // (warp-uniform)
+                float pv[32];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const uint32_t* kp = reinterpret_cast<const uint32_t*>(&wa[u]);
-#pragma unroll
-                for (int z = 0; z < 4; z++) {
-                    const float2 kk = unpack_h16x2(kp[z], bf);
-                    acc = fmaf(qs[(u * 4 + z) * 2], kk.x, acc);
-                    acc = fmaf(qs[(u * 4 + z) * 2 + 1], kk.y, acc);
+                for (int u = 0; u < 32; u++) {
+                    const float2 kk = unpack_h16x2(kr[half * 32 + u], bf);
+                    pv[u] = fmaf(qf.y, kk.y, qf.x * kk.x);
+                }
+                const float sc = af_transpose_reduce(pv, lane) * 0.125f;
+                const int j = j0 + half * 32 + lane;
+                if (j < t) {
+                    ps[j] = sc;
+                    m = fmaxf(m, sc);
                 }
             }
-            acc *= 0.125f;
-            ps[ja] = acc;
-            m = fmaxf(m, acc);
-        }
-        if (jb < t) {
-            float acc = 0.f;
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const uint32_t* kp = reinterpret_cast<const uint32_t*>(&wb[u]);
-#pragma unroll
-                for (int z = 0; z < 4; z++) {
-                    const float2 kk = unpack_h16x2(kp[z], bf);
-                    acc = fmaf(qs[(u * 4 + z) * 2], kk.x, acc);
-                    acc = fmaf(qs[(u * 4 + z) * 2 + 1], kk.y, acc);
-                }
-            }
-            acc *= 0.125f;
-            ps[jb] = acc;
-            m = fmaxf(m, acc);
         }
     }
     m = warp_max(m);
@@ -364,7 +357,7 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     __syncwarp();
     const float inv = 1.0f / sum;
     float2 o = make_float2(e_new * vf.x, e_new * vf.y);
-    for (int j0 = 0; j0 < t; j0 += 64) {                  // up to 64 V rows in flight (rows added in cache order: same sum order)
+    for (int j0 = 0; j0 < t; j0 += 64) {                  // up to 64 V rows in flight (rows added in cache order)
         uint32_t raw[64];
 #pragma unroll
         for (int u = 0; u < 64; u++)
@@ -387,17 +380,21 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
 // single-step buffers).  One CTA per (group, head); the group's K and V rows are staged in shared memory (row stride 66 elements:
 // conflict-free for lane <-> key), warp <-> query, lane <-> key for the scores and lane <-> 2 dims for the output -- the same
 // arithmetic order as attn_fast_kernel's.  When kc != NULL the K / V rows are also written to the cache [g][head][t][64].
-constexpr int PA_MAXT = 128;
+constexpr int PA_MAXT = 512;
+static size_t prefill_attn_smem(int T) { return ((size_t)2 * T * 33 + 4 * 64 + (size_t)4 * T) * 4; }
 __global__ void __launch_bounds__(128)
 prefill_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ kc, h16* __restrict__ vc, h16* __restrict__ att, int G, int T, int E,
                     int nh, int Tmax, int bf) {
-    __shared__ uint32_t ks[PA_MAXT][33], vs[PA_MAXT][33];
-    __shared__ float qs[4][64];
-    __shared__ float ps[4][PA_MAXT];
+    extern __shared__ uint32_t pa_smem[];
+    uint32_t (*ks)[33] = reinterpret_cast<uint32_t (*)[33]>(pa_smem);
+    uint32_t (*vs)[33] = reinterpret_cast<uint32_t (*)[33]>(pa_smem + (size_t)T * 33);
+    float (*qs)[64] = reinterpret_cast<float (*)[64]>(pa_smem + (size_t)2 * T * 33);
+    float* ps_all = reinterpret_cast<float*>(pa_smem + (size_t)2 * T * 33 + 4 * 64);
     tc::pdl_launch_dependents();
     tc::pdl_wait();
     const int g = blockIdx.x / nh, h = blockIdx.x % nh;
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    float* ps = ps_all + (size_t)wq * T;
     for (int i = threadIdx.x; i < T * 32; i += 128) {
         const int t = i >> 5, c2 = i & 31;
         const h16* row = qkv + ((int64_t)t * G + g) * 3 * E + h * 64 + 2 * c2;
@@ -426,14 +423,14 @@ prefill_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ kc, h16* __re
                 acc = fmaf(qs[wq][2 * u + 1], kk.y, acc);
             }
             acc *= 0.125f;
-            ps[wq][j] = acc;
+            ps[j] = acc;
             m = fmaxf(m, acc);
         }
         m = warp_max(m);
         float sum = 0.f;
         for (int j = lane; j <= t; j += 32) {
-            const float e = __expf(ps[wq][j] - m);
-            ps[wq][j] = e;
+            const float e = __expf(ps[j] - m);
+            ps[j] = e;
             sum += e;
         }
         sum = warp_sum(sum);
@@ -441,8 +438,8 @@ prefill_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ kc, h16* __re
         float2 o = make_float2(0.f, 0.f);
         for (int j = 0; j <= t; j++) {
             const float2 vv = unpack_h16x2(vs[j][lane], bf);
-            o.x = fmaf(ps[wq][j], vv.x, o.x);
-            o.y = fmaf(ps[wq][j], vv.y, o.y);
+            o.x = fmaf(ps[j], vv.x, o.x);
+            o.y = fmaf(ps[j], vv.y, o.y);
         }
         const float inv = 1.0f / sum;
         *reinterpret_cast<uint32_t*>(att + ((int64_t)t * G + g) * E + h * 64 + 2 * lane) = pack_h16x2(o.x * inv, o.y * inv, bf);
@@ -465,7 +462,7 @@ cond_tok_kernel(const StepState* __restrict__ stt, const float* __restrict__ con
 }
 // summed code embeddings in 16-bit: mode 0 -> all D codes of position idx-1 (body input), mode d>=1 -> codes 0..d-1 of
 // position idx (head input, cumsum)                                              (transformers.py:219-225, 250-255)
-// mode < 0 (prefill / forward): grid (B, n_pos); all D codes of position blockIdx.y + pos0, written to row blockIdx.y * B + b
+// mode < 0 (prefill / forward): grid (B, n_pos); the first -mode codes of position blockIdx.y + pos0, written to row blockIdx.y * B + b
 __global__ void __launch_bounds__(64)
 code_sum_kernel(const StepState* __restrict__ stt, const float* __restrict__ cb, int HW, int D, int K, int C, int mode, int pos0,
                 h16* __restrict__ out, int bf) {
@@ -473,7 +470,7 @@ code_sum_kernel(const StepState* __restrict__ stt, const float* __restrict__ cb,
     tc::pdl_wait();
     const int b = blockIdx.x, B = gridDim.x;
     const int pos = mode < 0 ? pos0 + blockIdx.y : (mode == 0 ? stt->idx - 1 : stt->idx);
-    const int nd = mode <= 0 ? D : mode;
+    const int nd = mode == 0 ? D : (mode < 0 ? -mode : mode);
     h16* o = out + ((int64_t)blockIdx.y * B + b) * C;
     for (int c = threadIdx.x; c < C; c += 64) {
         float a = 0.f;
@@ -520,7 +517,7 @@ struct ArFast {
     rqb200_ar_weights w;
     std::vector<rqb200_block_weights> body, head;
     std::vector<FastLayer> lbody, lhead;
-    CUtensorMap tm_win, tm_whead, tm_cls;
+    CUtensorMap tm_win, tm_whead, tm_cls, tm_ccls;
     int bf = 0;                          // 16-bit format: 0 fp16, 1 bf16
     // per (workspace, B) state
     void* ws_base = nullptr;
@@ -529,7 +526,7 @@ struct ArFast {
     cudaGraphExec_t graphs[G_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     int64_t n_nodes[G_COUNT] = {0, 0, 0, 0};   // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
-    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, next_pf = true, ln_cluster = false;
+    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, next_pf = true, ln_cluster = false, kv_pf = true;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
     int n_sm = 148;
     // diagnostic stage trace (cfg.flags & RQB200_AR_TRACE)
@@ -647,13 +644,15 @@ static int ln(const ArFast& f, const char* name, int rows, const float* x_in, co
 }
 
 static int attn(const ArFast& f, FastWs& ws, const float* bqkv, h16* kc, h16* vc, int Tmax, const int* t_ptr, int t_host,
-                cudaStream_t st) {
+                const h16* kc_next, const h16* vc_next, bool first, cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
-    const size_t smem = (size_t)(4 * 64 + 4 * ((Tmax + 31) & ~31)) * sizeof(float);
+    const size_t smem = (size_t)(4 * ((Tmax + 31) & ~31)) * sizeof(float);
     // reading the position counter ahead of the dependency is only safe inside a captured graph (see the kernel)
+    const int early = (f.use_graph || t_ptr == nullptr) ? 1 : 0;
     return launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(f.B * c.n_head, 4)), dim3(128), smem, st, f.use_pdl,
-                      (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, t_ptr, t_host,
-                      (f.use_graph || t_ptr == nullptr) ? 1 : 0, f.bf, tr_slot(f, "attn"));
+                      (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, t_ptr, t_host, early,
+                      f.kv_pf ? kc_next : (const h16*)nullptr, f.kv_pf ? vc_next : (const h16*)nullptr, (first || !f.kv_pf) ? 1 : 0, f.bf,
+                      tr_slot(f, "attn"));
 }
 
 // one transformer stack on the single new token of every batch row; x lives in `x` (fp32); residual additions are deferred
@@ -676,7 +675,9 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
                    first ? pending_extra : nof, x, bw.ln1_w, bw.ln1_b, ws.XN, st));
         RQB_TRY(gemm(f, "qkv", maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr, 0,
                      st));
-        RQB_TRY(attn(f, ws, bw.bqkv, kc + per * l, vc + per * l, Tmax, t_ptr, t_host, st));
+        const bool has_next = l + 1 < blocks.size();
+        RQB_TRY(attn(f, ws, bw.bqkv, kc + per * l, vc + per * l, Tmax, t_ptr, t_host, has_next ? kc + per * (l + 1) : nullptr,
+                     has_next ? vc + per * (l + 1) : nullptr, first, st));
         RQB_TRY(gemm(f, "proj", maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr,
                      0, st));
         RQB_TRY(ln(f, "ln2", B, x, ws.P, f.split_proj, bw.bproj, nof, x, bw.ln2_w, bw.ln2_b, ws.XN, st));
@@ -800,6 +801,7 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     f->batched_prefill = !(cfg.flags & RQB200_AR_SEQUENTIAL_PREFILL);
     f->next_pf = !(cfg.flags & RQB200_AR_NO_NEXT_PREFETCH);
     f->ln_cluster = (cfg.flags & RQB200_AR_LN_CLUSTER) != 0;
+    f->kv_pf = !(cfg.flags & RQB200_AR_NO_KV_PREFETCH);
     {
         int dev = 0, n = 0;
         cudaGetDevice(&dev);
@@ -825,6 +827,7 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     if (!rc) rc = make_tmap_weight(&f->tm_win, w.w_in, E, cfg.code_dim);
     if (!rc) rc = make_tmap_weight(&f->tm_whead, w.w_head, E, cfg.code_dim);
     if (!rc) rc = make_tmap_weight(&f->tm_cls, w.w_cls, cfg.vocab, E);
+    if (!rc && w.w_ccls) rc = make_tmap_weight(&f->tm_ccls, w.w_ccls, (cfg.vocab_cond + 127) / 128 * 128, E);
     if (rc) { delete f; return nullptr; }
     for (int i = 0; i <= G_COUNT; i++) f->tr_graph_base[i] = i * (TR_CAP / G_COUNT);
     return f;
@@ -839,75 +842,189 @@ void ar_fast_destroy(ArFast* f) {
 
 size_t ar_fast_workspace_bytes(const ArFast* f, int B) { return fast_layout(*f, B, nullptr, 0, nullptr); }
 
-// ---- batched prefill: body tokens [s0, s0 + T) of every batch row in one pass (rows token-major: row = t * B + b).
-// Token s < cond_len is a cond token; token s >= cond_len carries the codes of position s - cond_len.  Requires s0 == 0
-// (the causal attention kernel sees the whole prefix) and T <= PA_MAXT.  Leaves ws.XB = the last token's output rows, the KV
+// ---- batched passes (prefill, teacher-forced forward): M = G * T token rows, token-major (row = t * G + g), through one stack.
+struct BatchBufs {
+    float* X;                    // [M, E] residual stream (in / out)
+    h16 *XN, *QKV, *ATT, *H;     // [M,E], [M,3E], [M,E], [M,4E] scratch
+};
+
+static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blocks, const std::vector<FastLayer>& maps,
+                         const BatchBufs& bb, int G, int T, h16* kc, h16* vc, int64_t kv_per_layer, int Tmax, cudaStream_t st) {
+    const rqb200_ar_config& c = f.cfg;
+    const int E = c.embed_dim;
+    const int64_t M = (int64_t)G * T;
+    if (M > (int64_t)1 << 30 || T > PA_MAXT) return fail(RQB200_EINVAL, "ar fast tier: batched pass too large");
+    const bool pdl = false;              // large launches: plain stream order
+    CUtensorMap tx_xn, tx_att, tx_h;
+    const int bn = gemm_tc_bn((int)std::min<int64_t>(M, 256));
+    RQB_TRY(make_tmap_2d(&tx_xn, bb.XN, 1, E, M, (uint64_t)E * 2, 64, bn));
+    RQB_TRY(make_tmap_2d(&tx_att, bb.ATT, 1, E, M, (uint64_t)E * 2, 64, bn));
+    RQB_TRY(make_tmap_2d(&tx_h, bb.H, 1, 4 * E, M, (uint64_t)E * 8, 64, bn));
+    RQB_ENSURE_SMEM(prefill_attn_smem(PA_MAXT), prefill_attn_kernel);
+    const float* nof = nullptr;
+    for (size_t l = 0; l < blocks.size(); l++) {
+        const rqb200_block_weights& bw = blocks[l];
+        RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, bw.ln1_w, bw.ln1_b, bb.XN, st));
+        {
+            GemmTcParams p = gemm_base(f, 3 * E, E, (int)M, 1, GT_H16);
+            p.bias = bw.bqkv; p.out = bb.QKV;
+            RQB_TRY(launch_gemm_tc(maps[l].qkv, tx_xn, p, pdl, st));
+        }
+        RQB_TRY(launch_pdl(prefill_attn_kernel, dim3((unsigned)(G * c.n_head)), dim3(128), prefill_attn_smem(T), st, pdl,
+                           (const h16*)bb.QKV, kc ? kc + kv_per_layer * l : nullptr, vc ? vc + kv_per_layer * l : nullptr, bb.ATT, G, T, E,
+                           c.n_head, Tmax, f.bf));
+        {
+            GemmTcParams p = gemm_base(f, E, E, (int)M, 1, GT_F32);
+            p.bias = bw.bproj; p.out = bb.X; p.residual = bb.X; p.ld_res = E;
+            RQB_TRY(launch_gemm_tc(maps[l].proj, tx_att, p, pdl, st));
+        }
+        RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, bw.ln2_w, bw.ln2_b, bb.XN, st));
+        {
+            GemmTcParams p = gemm_base(f, 4 * E, E, (int)M, 1, GT_H16_GELU);
+            p.bias = bw.b1; p.out = bb.H;
+            RQB_TRY(launch_gemm_tc(maps[l].fc1, tx_xn, p, pdl, st));
+        }
+        {
+            GemmTcParams p = gemm_base(f, E, 4 * E, (int)M, 1, GT_F32);
+            p.bias = bw.b2; p.out = bb.X; p.residual = bb.X; p.ld_res = E;
+            RQB_TRY(launch_gemm_tc(maps[l].fc2, tx_h, p, pdl, st));
+        }
+    }
+    return 0;
+}
+
+// body input tokens [0, T) of every batch row into X (token-major): token s < cond_len is a cond token (transformers.py:224),
+// token s >= cond_len carries the summed input embeddings of the codes of position s - cond_len (:219-225)
+static int body_tokens_batched(ArFast& f, const StepState* state, float* X, h16* S, int B, int T, cudaStream_t st) {
+    const rqb200_ar_config& c = f.cfg;
+    const rqb200_ar_weights& w = f.w;
+    const int E = c.embed_dim, HW = c.H * c.W, cl = c.cond_len;
+    RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B, std::min(T, cl)), dim3(256), (size_t)0, st, false, state, w.cond_emb, w.pos_emb_cond, cl,
+                       c.vocab_cond, E, X));
+    const int n_code = T - cl;       // code tokens of positions 0 .. n_code-1
+    if (n_code > 0) {
+        const int64_t Mc = (int64_t)B * n_code;
+        CUtensorMap tx_s;
+        RQB_TRY(make_tmap_2d(&tx_s, S, 1, c.code_dim, Mc, (uint64_t)c.code_dim * 2, 64, gemm_tc_bn((int)std::min<int64_t>(Mc, 256))));
+        RQB_TRY(launch_pdl(code_sum_kernel, dim3(B, n_code), dim3(64), (size_t)0, st, false, state, w.codebook, HW, c.D, c.codebook_size,
+                           c.code_dim, -c.D, 0, S, f.bf));
+        GemmTcParams p = gemm_base(f, E, c.code_dim, (int)Mc, 1, GT_F32);
+        p.bias = w.b_in; p.bias_scale = (float)c.D; p.out = X + (int64_t)cl * B * E;
+        p.residual = w.pos_emb_hw; p.ld_res = E; p.res_div = B;          // row (j, b) gets pos_emb_hw[j]
+        RQB_TRY(launch_gemm_tc(f.tm_win, tx_s, p, false, st));
+    }
+    return 0;
+}
+
+// ---- batched prefill: body tokens [0, T) of every batch row in one pass.  Leaves ws.XB = the last token's output rows, the KV
 // cache rows [0, T) written, state.s = T.
 static int prefill_batched(ArFast& f, FastWs& ws, int T, cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
-    const rqb200_ar_weights& w = f.w;
     const int E = c.embed_dim, B = f.B, HW = c.H * c.W, cl = c.cond_len, Tb = cl + HW;
     const int64_t M = (int64_t)B * T;
     if (M > ws.Mmax || T > PA_MAXT) return fail(RQB200_EINVAL, "ar fast tier: prefix too long for the batched prefill");
-    const bool pdl = false;              // large launches: plain stream order
-    CUtensorMap tx_xn, tx_att, tx_h, tx_s;
-    const int bn = gemm_tc_bn((int)std::min<int64_t>(M, 256));
-    RQB_TRY(make_tmap_2d(&tx_xn, ws.PXN, 1, E, M, (uint64_t)E * 2, 64, bn));
-    RQB_TRY(make_tmap_2d(&tx_att, ws.PATT, 1, E, M, (uint64_t)E * 2, 64, bn));
-    RQB_TRY(make_tmap_2d(&tx_h, ws.PH, 1, 4 * E, M, (uint64_t)E * 8, 64, bn));
     const bool save_pdl = f.use_pdl, save_tr = f.trace;
-    f.use_pdl = pdl;
+    f.use_pdl = false;
     f.trace = false;
     int rc = [&]() -> int {
-        // tokens
-        RQB_TRY(launch_pdl(cond_tok_kernel, dim3(B, std::min(T, cl)), dim3(256), (size_t)0, st, pdl, (const StepState*)ws.state, w.cond_emb,
-                           w.pos_emb_cond, cl, c.vocab_cond, E, ws.PX));
-        const int n_code = T - cl;       // code tokens of positions 0 .. n_code-1
-        if (n_code > 0) {
-            const int64_t Mc = (int64_t)B * n_code;
-            RQB_TRY(make_tmap_2d(&tx_s, ws.PS, 1, c.code_dim, Mc, (uint64_t)c.code_dim * 2, 64, gemm_tc_bn((int)std::min<int64_t>(Mc, 256))));
-            RQB_TRY(launch_pdl(code_sum_kernel, dim3(B, n_code), dim3(64), (size_t)0, st, pdl, (const StepState*)ws.state, w.codebook, HW,
-                               c.D, c.codebook_size, c.code_dim, -1, 0, ws.PS, f.bf));
-            GemmTcParams p = gemm_base(f, E, c.code_dim, (int)Mc, 1, GT_F32);
-            p.bias = w.b_in; p.bias_scale = (float)c.D; p.out = ws.PX + (int64_t)cl * B * E;
-            p.residual = w.pos_emb_hw; p.ld_res = E; p.res_div = B;          // row (j, b) gets pos_emb_hw[j]
-            RQB_TRY(launch_gemm_tc(f.tm_win, tx_s, p, pdl, st));
-        }
-        const float* nof = nullptr;
-        for (size_t l = 0; l < f.body.size(); l++) {
-            const rqb200_block_weights& bw = f.body[l];
-            const int64_t per = (int64_t)B * c.n_head * Tb * 64;
-            RQB_TRY(ln(f, "", (int)M, ws.PX, nof, 0, nof, nof, nullptr, bw.ln1_w, bw.ln1_b, ws.PXN, st));
-            {
-                GemmTcParams p = gemm_base(f, 3 * E, E, (int)M, 1, GT_H16);
-                p.bias = bw.bqkv; p.out = ws.PQKV;
-                RQB_TRY(launch_gemm_tc(f.lbody[l].qkv, tx_xn, p, pdl, st));
-            }
-            RQB_TRY(launch_pdl(prefill_attn_kernel, dim3((unsigned)(B * c.n_head)), dim3(128), (size_t)0, st, pdl, (const h16*)ws.PQKV,
-                               ws.kc_body + per * l, ws.vc_body + per * l, ws.PATT, B, T, E, c.n_head, Tb, f.bf));
-            {
-                GemmTcParams p = gemm_base(f, E, E, (int)M, 1, GT_F32);
-                p.bias = bw.bproj; p.out = ws.PX; p.residual = ws.PX; p.ld_res = E;
-                RQB_TRY(launch_gemm_tc(f.lbody[l].proj, tx_att, p, pdl, st));
-            }
-            RQB_TRY(ln(f, "", (int)M, ws.PX, nof, 0, nof, nof, nullptr, bw.ln2_w, bw.ln2_b, ws.PXN, st));
-            {
-                GemmTcParams p = gemm_base(f, 4 * E, E, (int)M, 1, GT_H16_GELU);
-                p.bias = bw.b1; p.out = ws.PH;
-                RQB_TRY(launch_gemm_tc(f.lbody[l].fc1, tx_xn, p, pdl, st));
-            }
-            {
-                GemmTcParams p = gemm_base(f, E, 4 * E, (int)M, 1, GT_F32);
-                p.bias = bw.b2; p.out = ws.PX; p.residual = ws.PX; p.ld_res = E;
-                RQB_TRY(launch_gemm_tc(f.lbody[l].fc2, tx_h, p, pdl, st));
-            }
-        }
+        RQB_TRY(body_tokens_batched(f, ws.state, ws.PX, ws.PS, B, T, st));
+        BatchBufs bb = {ws.PX, ws.PXN, ws.PQKV, ws.PATT, ws.PH};
+        RQB_TRY(stack_batched(f, f.body, f.lbody, bb, B, T, ws.kc_body, ws.vc_body, (int64_t)B * c.n_head * Tb * 64, Tb, st));
         RQB_CUDA(cudaMemcpyAsync(ws.XB, ws.PX + (int64_t)(T - 1) * B * E, (size_t)B * E * sizeof(float), cudaMemcpyDeviceToDevice, st));
         RQB_TRY(launch_pdl(advance_kernel, dim3(1), dim3(32), (size_t)0, st, false, ws.state, T, 0, 0));
         return 0;
     }();
     f.use_pdl = save_pdl;
     f.trace = save_tr;
+    return rc;
+}
+
+// ---- teacher-forced forward (transformers.py:113-188): all H*W*D logits of given code maps in a handful of large-M GEMM passes.
+// Body: T = cond_len + H*W - 1 tokens per batch row (M = B*T rows); head: for every (position, batch row) a group of D tokens
+// [spatial ctx + pos_d[0], head_mlp(cumsum_{i<d} e_i) + pos_d[d]] (M = D * H*W * B rows, causal attention inside each group).
+// logits_out [D][H*W][B][V] f32 (token-major; the host permutes), cond_logits_out (nullable) [cond_len-1][B][vocab_cond rounded
+// up to a multiple of 128] (the cond classifier's weight / bias rows are zero-padded to that size by the caller).
+struct FwdWs {
+    StepState* state;
+    float *BX, *HX;
+    h16 *XN, *QKV, *ATT, *H, *S;
+};
+static size_t forward_layout(const ArFast& f, int B, void* base, size_t cap, FwdWs* out) {
+    const rqb200_ar_config& c = f.cfg;
+    Arena a(base, cap);
+    const int64_t E = c.embed_dim, HW = (int64_t)c.H * c.W, Tb = c.cond_len + HW - 1;
+    const int64_t Mb = B * Tb, Mh = (int64_t)c.D * HW * B, Mm = std::max(Mb, Mh);
+    FwdWs w;
+    w.state = a.take<StepState>(1);
+    w.BX = a.take<float>(Mb * E);
+    w.HX = a.take<float>(Mh * E);
+    w.XN = a.take<h16>(Mm * E);
+    w.QKV = a.take<h16>(Mm * 3 * E);
+    w.ATT = a.take<h16>(Mm * E);
+    w.H = a.take<h16>(Mm * 4 * E);
+    w.S = a.take<h16>(HW * B * c.code_dim);
+    if (out) *out = w;
+    return a.off + 256;
+}
+size_t ar_fast_forward_workspace_bytes(const ArFast* f, int B) { return forward_layout(*f, B, nullptr, 0, nullptr); }
+
+int ar_fast_forward(ArFast* f, const int64_t* codes, const int64_t* cond, int B, float* logits_out, float* cond_logits_out, void* wsp,
+                    size_t ws_bytes, cudaStream_t st) {
+    const rqb200_ar_config& c = f->cfg;
+    const rqb200_ar_weights& w = f->w;
+    const int E = c.embed_dim, D = c.D, HW = c.H * c.W, cl = c.cond_len, V = c.vocab, Tb = cl + HW - 1;
+    if (B < 1) return fail(RQB200_EINVAL, "ar_forward: B must be > 0");
+    if (Tb > PA_MAXT) return fail(RQB200_EINVAL, "ar_forward: sequence too long for the batched attention kernel");
+    if (cond_logits_out && (cl < 2 || !w.w_ccls)) return fail(RQB200_EINVAL, "ar_forward: cond logits need cond_len > 1 and a cond classifier");
+    FwdWs ws;
+    if (forward_layout(*f, B, wsp, ws_bytes, &ws) > ws_bytes) return fail(RQB200_EWORKSPACE, "ar_forward: workspace too small");
+    StepState h = {};
+    h.cond = cond; h.codes = const_cast<int64_t*>(codes);
+    RQB_TRY(launch_pdl(init_state_kernel, dim3(1), dim3(32), (size_t)0, st, false, ws.state, h, 0));
+    const bool save_pdl = f->use_pdl, save_tr = f->trace;
+    f->use_pdl = false;
+    f->trace = false;
+    const float* nof = nullptr;
+    int rc = [&]() -> int {
+        const int G = HW * B;                                  // head groups, g = pos * B + b
+        const int64_t Mh = (int64_t)D * G;
+        // body
+        RQB_TRY(body_tokens_batched(*f, ws.state, ws.BX, ws.S, B, Tb, st));
+        BatchBufs bb = {ws.BX, ws.XN, ws.QKV, ws.ATT, ws.H};
+        RQB_TRY(stack_batched(*f, f->body, f->lbody, bb, B, Tb, nullptr, nullptr, 0, Tb, st));
+        if (cond_logits_out) {                                  // cond_classifier(latents[:, :cond_len-1])        (:153-156)
+            const int64_t Mc = (int64_t)(cl - 1) * B;
+            CUtensorMap tx;
+            RQB_TRY(make_tmap_2d(&tx, ws.XN, 1, E, Mc, (uint64_t)E * 2, 64, gemm_tc_bn((int)std::min<int64_t>(Mc, 256))));
+            RQB_TRY(ln(*f, "", (int)Mc, ws.BX, nof, 0, nof, nof, nullptr, w.ccls_ln_w, w.ccls_ln_b, ws.XN, st));
+            GemmTcParams p = gemm_base(*f, (c.vocab_cond + 127) / 128 * 128, E, (int)Mc, 1, GT_F32);
+            p.bias = w.b_ccls; p.out = cond_logits_out;
+            RQB_TRY(launch_gemm_tc(f->tm_ccls, tx, p, false, st));
+        }
+        // head tokens: d = 0 rows = spatial ctx (body rows of tokens cond_len-1 ..) + pos_emb_d[0]; d >= 1 rows = head_mlp(cumsum)
+        RQB_TRY(ln(*f, "", G, ws.BX + (int64_t)(cl - 1) * B * E, nof, 0, nof, w.pos_emb_d, ws.HX, nof, nof, nullptr, st));
+        CUtensorMap tx_s;
+        RQB_TRY(make_tmap_2d(&tx_s, ws.S, 1, c.code_dim, G, (uint64_t)c.code_dim * 2, 64, gemm_tc_bn(std::min(G, 256))));
+        for (int d = 1; d < D; d++) {
+            RQB_TRY(launch_pdl(code_sum_kernel, dim3(B, HW), dim3(64), (size_t)0, st, false, (const StepState*)ws.state, w.codebook, HW, D,
+                               c.codebook_size, c.code_dim, -d, 0, ws.S, f->bf));
+            GemmTcParams p = gemm_base(*f, E, c.code_dim, G, 1, GT_F32);
+            p.bias = w.b_head; p.out = ws.HX + (int64_t)d * G * E; p.residual = w.pos_emb_d + (int64_t)d * E; p.ld_res = 0;
+            RQB_TRY(launch_gemm_tc(f->tm_whead, tx_s, p, false, st));
+        }
+        BatchBufs hb = {ws.HX, ws.XN, ws.QKV, ws.ATT, ws.H};
+        RQB_TRY(stack_batched(*f, f->head, f->lhead, hb, G, D, nullptr, nullptr, 0, D, st));
+        // classifier                                                                                   (:181-183)
+        CUtensorMap tx;
+        RQB_TRY(make_tmap_2d(&tx, ws.XN, 1, E, Mh, (uint64_t)E * 2, 64, gemm_tc_bn((int)std::min<int64_t>(Mh, 256))));
+        RQB_TRY(ln(*f, "", (int)Mh, ws.HX, nof, 0, nof, nof, nullptr, w.cls_ln_w, w.cls_ln_b, ws.XN, st));
+        GemmTcParams p = gemm_base(*f, V, E, (int)Mh, 1, GT_F32);
+        p.bias = w.b_cls; p.out = logits_out;
+        RQB_TRY(launch_gemm_tc(f->tm_cls, tx, p, false, st));
+        return 0;
+    }();
+    f->use_pdl = save_pdl;
+    f->trace = save_tr;
     return rc;
 }
 

@@ -120,6 +120,9 @@ size_t ar_fast_workspace_bytes(const ArFast* f, int B);
 int ar_fast_sample(ArFast* f, const int64_t* partial, const int64_t* cond, int B, int idx_begin, int idx_end, int resume,
                    float temperature, const int32_t* top_k, const float* top_p, const float* noise, int64_t noise_stride,
                    float* logits_out, const int64_t* force, int64_t* out, void* wsp, size_t ws_bytes, cudaStream_t st);
+size_t ar_fast_forward_workspace_bytes(const ArFast* f, int B);
+int ar_fast_forward(ArFast* f, const int64_t* codes, const int64_t* cond, int B, float* logits_out, float* cond_logits_out, void* wsp,
+                    size_t ws_bytes, cudaStream_t st);
 // diagnostics: copies the stage trace of the last replays to the host (RQB200 ar_config.trace); returns the number of launches traced
 int ar_fast_trace(ArFast* f, long long* out_host, int cap_launches, char* names, int names_cap);
 }  // namespace rqb

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("RQB200_LIB", os.path.join(os.path.dirname(_HERE), "cs
 OK, EINVAL, ECUDA, ENODEV, EWORKSPACE, ESTATE = 0, -1, -2, -3, -4, -5
 F32, BF16, F16 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
-AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_NO_NEXT_PREFETCH, AR_LN_CLUSTER = 1, 2, 4, 8, 16, 32, 64, 128
+AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_NO_NEXT_PREFETCH, AR_LN_CLUSTER, AR_NO_KV_PREFETCH = 1, 2, 4, 8, 16, 32, 64, 128, 256
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 c_f32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p
@@ -30,7 +30,8 @@ class ArConfig(C.Structure):
 class ArWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("pos_emb_cond", "pos_emb_hw", "pos_emb_d", "cond_emb", "w_in", "w_head", "w_cls",
                                           "b_in", "b_head", "b_cls", "cls_ln_w", "cls_ln_b", "codebook")] + \
-               [("body", C.POINTER(BlockWeights)), ("head", C.POINTER(BlockWeights))]
+               [("body", C.POINTER(BlockWeights)), ("head", C.POINTER(BlockWeights))] + \
+               [(n, C.c_void_p) for n in ("w_ccls", "b_ccls", "ccls_ln_w", "ccls_ln_b")]
 
 
 class VaeConfig(C.Structure):
@@ -80,6 +81,10 @@ def lib():
     L.rqb200_ar_sample_span.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                         C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.rqb200_ar_forward_workspace_bytes.restype = C.c_size_t
+    L.rqb200_ar_forward_workspace_bytes.argtypes = [C.c_void_p, C.c_int]
+    L.rqb200_ar_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]
     L.rqb200_ar_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     L.rqb200_ar_last_launches.restype = C.c_int64
     L.rqb200_ar_last_launches.argtypes = [C.c_void_p]
@@ -107,7 +112,8 @@ def lib():
 
 EXPORTS = ["rqb200_last_error", "rqb200_version", "rqb200_device_count", "rqb200_rq_quantize", "rqb200_rq_embed_sum",
            "rqb200_rq_embed_depth", "rqb200_sample_logits", "rqb200_ar_create", "rqb200_ar_destroy",
-           "rqb200_ar_workspace_bytes", "rqb200_ar_sample", "rqb200_ar_sample_span", "rqb200_ar_trace", "rqb200_ar_last_launches", "rqb200_vae_create",
+           "rqb200_ar_workspace_bytes", "rqb200_ar_sample", "rqb200_ar_sample_span", "rqb200_ar_forward",
+           "rqb200_ar_forward_workspace_bytes", "rqb200_ar_trace", "rqb200_ar_last_launches", "rqb200_vae_create",
            "rqb200_vae_destroy", "rqb200_vae_set_tensor", "rqb200_vae_finalize", "rqb200_vae_workspace_bytes",
            "rqb200_vae_decode", "rqb200_vae_decode_code", "rqb200_vae_encode", "rqb200_vae_last_launches",
            "rqb200_dbg_gemm_tc", "rqb200_dbg_conv_tc", "rqb200_dbg_chain", "rqb200_dbg_rq_quantize",
@@ -161,6 +167,7 @@ def ar_engine_options():
     flags |= AR_SEQUENTIAL_PREFILL if env("RQB200_SEQ_PREFILL", "0") == "1" else 0
     flags |= AR_NO_NEXT_PREFETCH if env("RQB200_NO_NEXT_PF", "0") == "1" else 0
     flags |= AR_LN_CLUSTER if env("RQB200_LN_CLUSTER", "0") == "1" else 0
+    flags |= AR_NO_KV_PREFETCH if env("RQB200_NO_KV_PF", "0") == "1" else 0
     return {"flags": flags,
             "splits": [int(env("RQB200_SPLIT_" + k, "0")) for k in ("QKV", "PROJ", "FC1", "FC2")]}
 

@@ -198,6 +198,12 @@ class RQTransformer(Stage2Model):
         w.w_cls, w.b_cls = wt(self.classifier.linear.weight), f32(self.classifier.linear.bias)
         w.cls_ln_w, w.cls_ln_b = f32(self.classifier.layer_norm.weight), f32(self.classifier.layer_norm.bias)
         w.codebook = f32(codebook)
+        if hasattr(self, "cond_classifier") and mode == N.MODE_FAST:
+            pad = -self.vocab_size_cond % 128            # classifier rows padded with zeros up to the 128-feature tcgen05 tile
+            pw = torch.nn.functional.pad(self.cond_classifier.linear.weight.detach(), (0, 0, 0, pad))
+            pb = torch.nn.functional.pad(self.cond_classifier.linear.bias.detach(), (0, pad))
+            w.w_ccls, w.b_ccls = wt(pw), f32(pb)
+            w.ccls_ln_w, w.ccls_ln_b = f32(self.cond_classifier.layer_norm.weight), f32(self.cond_classifier.layer_norm.bias)
         body, head = blocks(self.body_transformer), blocks(self.head_transformer)
         w.body, w.head = C.cast(body, C.POINTER(N.BlockWeights)), C.cast(head, C.POINTER(N.BlockWeights))
         keep.extend([body, head, cfg, w])
@@ -351,13 +357,45 @@ class RQTransformer(Stage2Model):
         return logits[(h * W + w) * D + d]
 
     def forward(self, xs, model_aux=None, cond=None, amp=False):
-        """transformers.py:113-188 -- teacher-forced logits [B,H,W,D,V] (cond_len == 1 return convention)."""
-        if self.block_size_cond > 1:
-            raise NotImplementedError("rqb200: cond_logits for cond_len > 1 are not produced by the sampling engine")
+        """transformers.py:113-188 -- teacher-forced logits [B,H,W,D,V]; with cond_len > 1 also the cond logits
+        [B,cond_len-1,vocab_cond] (the reference's return convention :185-188).
+        Fast tier (amp=True): all positions at once -- the body over B*(cond_len+H*W-1) rows, the head over B*H*W*D rows, as
+        large-M tcgen05 GEMMs + causal attention (rqb200_ar_forward).  Exact tier: the sequential teacher-forced replay."""
         B, H, W, D = xs.shape
+        if self._mode(amp) == N.MODE_FAST:
+            return self._native_forward(xs, model_aux, cond)
+        if self.block_size_cond > 1:
+            raise NotImplementedError("rqb200: cond_logits (cond_len > 1) are produced by the fast tier only (amp=True)")
         _, logits = self._native_sample(xs, model_aux, cond, (0, 0), 1.0, None, None, amp, noise=False,
                                         return_logits=True, force_codes=xs)
         return logits.reshape(H, W, D, B, -1).permute(3, 0, 1, 2, 4).contiguous()
+
+    @torch.no_grad()
+    def _native_forward(self, xs, model_aux, cond):
+        H, W, D = self.block_size
+        B = xs.shape[0]
+        dev = self.pos_emb_hw.device
+        N.require_cuda(xs, cond, self.pos_emb_hw)
+        codebook = self._codebook_of(model_aux, D)
+        eng = self._engine(codebook, N.MODE_FAST)
+        xs = xs.to(torch.int64).contiguous()
+        cl, V = self.block_size_cond, self.vocab_size[0]
+        cond_t = None if cond is None else cond.reshape(B, cl).to(torch.int64).contiguous()
+        want_cond = cl > 1 and hasattr(self, "cond_classifier")
+        with torch.cuda.device(dev):
+            need = N.lib().rqb200_ar_forward_workspace_bytes(eng["handle"], B)
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            logits = torch.empty(D, H * W, B, V, dtype=torch.float32, device=dev)
+            vcp = -(-self.vocab_size_cond // 128) * 128
+            cond_logits = torch.empty(cl - 1, B, vcp, dtype=torch.float32, device=dev) if want_cond else None
+            N.check(N.lib().rqb200_ar_forward(eng["handle"], N.ptr(xs), N.ptr(cond_t), B, N.ptr(logits), N.ptr(cond_logits), N.ptr(ws),
+                                              ws.numel(), N.stream_ptr(dev)), "ar_forward")
+            self.last_launches = N.lib().rqb200_ar_last_launches(eng["handle"])
+            N.launch_count["total"] += self.last_launches
+        out = logits.permute(2, 1, 0, 3).reshape(B, H, W, D, V).contiguous()
+        if want_cond:
+            return out, cond_logits[..., :self.vocab_size_cond].permute(1, 0, 2).contiguous()
+        return out
 
     def compute_loss(self, logits, targets, use_soft_target=False):
         return torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), targets.reshape(-1))

@@ -234,3 +234,40 @@ def test_fast_tier_large_batch_is_chunked(golden, layouts):
     full = model._native_sample(part, aux, cond, (0, 0), 1.0, 64, None, True, noise=noise)
     sub = model._native_sample(part[140:160], aux, cond[140:160], (0, 0), 1.0, 64, None, True, noise=noise[:, 140:160].contiguous())
     assert torch.equal(full[140:160], sub)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_txt", "cc3m654m"])
+def test_fast_tier_batched_forward(golden, layouts, name):
+    """RQTransformer.forward on the fast tier = a handful of large-M GEMM passes (body over B*(cond_len+H*W-1) rows, head over
+    B*H*W*D rows).  Against (a) the same tier's sequential teacher-forced replay, (b) the CPU oracle's forward (small shapes) incl.
+    the cond_classifier logits of a text-conditioned model (reference transformers.py:153-156,185-186)."""
+    from oracle import rq_oracle as O
+    g, model, aux, cond, bs, V = _case(name, golden, layouts)
+    E, nh, nb_, nhl, V_, bs_, vc, cl = AR_ZOO[name]
+    codes = g["runs"][-1]["codes"].long().to(DEV)
+    B = codes.shape[0]
+    model.precision = "fast"
+    out = model(codes, model_aux=aux, cond=cond, amp=True)
+    cond_logits = None
+    if isinstance(out, tuple):
+        out, cond_logits = out
+    assert out.shape == (B, *bs, V)
+    _, seq = model._native_sample(codes, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=codes)
+    seq = seq.reshape(*bs, B, V).permute(3, 0, 1, 2, 4)
+    std = float(seq.std())
+    d = float((out - seq).abs().max())
+    print("%s: batched forward vs sequential replay (fp16 tier): max logit difference %.2e (std %.3f)" % (name, d, std))
+    assert d < 0.02 * std
+    if E <= 128:
+        sd = {k: v.cpu() for k, v in model.state_dict().items()}
+        ref = O.ar_forward(sd, O.ArConfig(E, nh, nb_, nhl, V_, bs_, vc, cl), codes.cpu(), aux.quantizer._shared_table().cpu(),
+                           None if cond is None else cond.cpu())
+        assert float((out.cpu() - ref).abs().max()) < 0.04 * std
+    if cl > 1:
+        assert cond_logits is not None and cond_logits.shape == (B, cl - 1, vc)
+        sd = {k: v.cpu() for k, v in model.state_dict().items()}
+        _, cref = O.ar_forward(sd, O.ArConfig(E, nh, nb_, nhl, V_, bs_, vc, cl), codes.cpu(), aux.quantizer._shared_table().cpu(),
+                               cond.cpu(), with_cond_logits=True)
+        e = float((cond_logits.cpu() - cref).abs().max())
+        print("%s: cond_logits vs oracle: max error %.2e (std %.3f)" % (name, e, float(cref.std())))
+        assert e < 0.04 * float(cref.std())

@@ -183,7 +183,13 @@ def cpu_reference_leg(name, steps, warmup, budget_s, B):
     from oracle import rq_oracle as O
     E, nh, nb, nhl, V, bs, vc, cl = MODELS[name][:8]
     top_p = MODELS[name][10]
-    torch.set_num_threads(os.cpu_count() or 1)           # torchrun exports OMP_NUM_THREADS=1
+    # all physical cores this process may run on (torchrun exports OMP_NUM_THREADS=1; 2 hardware threads per core on the GPU hosts:
+    # one torch thread per logical CPU measured 30x slower here)
+    try:
+        logical = len(os.sched_getaffinity(0))
+    except AttributeError:
+        logical = os.cpu_count() or 1
+    torch.set_num_threads(max(1, logical // 2 if logical >= 16 else logical))
     cores = torch.get_num_threads()
     torch.manual_seed(0)
     ar, vae, dd = build_models(name, "cpu", "exact")
@@ -254,7 +260,8 @@ def parity_record(name, dev):
     aux = CodebookAux(synth.randn_seeded((V, 256), g["codebook_seed"]).to(dev))
     B = g["B"]
     cond = synth.randint_seeded(0, max(vc, 1), (B, cl), g["cond_seed"]).to(dev) if vc > 1 else None
-    codes = g["runs"][-1]["codes"].long().to(dev)
+    ref_run = next((r for r in g["runs"] if r["logits"]), g["runs"][-1])      # a trajectory the reference stored logits for
+    codes = ref_run["codes"].long().to(dev)
     tf = dict(noise=False, return_logits=True, force_codes=codes)
     model.precision = "exact"
     _, lg32 = model._native_sample(codes, aux, cond, (0, 0), 1.0, None, None, False, **tf)
@@ -266,9 +273,8 @@ def parity_record(name, dev):
     outside = differ & ((top2[..., 0] - top2[..., 1]) > 2 * err.amax(-1))
     std = float(lg32.std())
     ref_err = None
-    for run in g["runs"]:
-        if run["logits"] and torch.equal(run["codes"].long().to(dev), codes):
-            ref_err = max(float((lg16[s].cpu() - lg).abs().max()) for s, lg in run["logits"].items())
+    if ref_run["logits"]:
+        ref_err = max(float((lg16[s].cpu() - lg).abs().max()) for s, lg in ref_run["logits"].items())
     n_tok = bs[0] * bs[1] * bs[2]
     free = []
     for run in g["runs"]:
@@ -282,7 +288,7 @@ def parity_record(name, dev):
     del model
     torch.cuda.empty_cache()
     return {"reference_fixture": "tests/golden/ar.pt[%s] (B=%d, unmodified reference, fp32)" % (name, B),
-            "teacher_forced": {"logit_std": std, "err_rms_over_std": float(err.pow(2).mean().sqrt()) / std,
+            "teacher_forced": {"trajectory": {k: v for k, v in ref_run["setting"].items()}, "logit_std": std, "err_rms_over_std": float(err.pow(2).mean().sqrt()) / std,
                                "err_max_over_std": float(err.max()) / std, "max_err_vs_reference_logits": ref_err,
                                "greedy_flips": int(differ.sum()), "greedy_flips_outside_margin": int(outside.sum()),
                                "steps": int(differ.numel())},

@@ -218,6 +218,12 @@ int rqb200_dbg_conv_tc(const void* X16, const void* W16, const void* X16lo, cons
 int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, int smem_bytes, int fan, int reps, void* workspace,
                      size_t workspace_bytes, float* us_per_stage);
 
+/* rqb200_dbg_tma_rate: micro-benchmark of one SM's shared-memory fill rate from L2 (csrc/dbg_tma.cu).  mode 0: tensor-map boxes
+ * of `rows` x 128 B (what the GEMM kernels issue); mode 1: 1-D bulk copies of rows*128 contiguous bytes.  `depth` loads in flight,
+ * `iters` rounds, every CTA cycling over the same `boxes_total` boxes of `buffer` (>= boxes_total*rows*128 bytes). */
+int rqb200_dbg_tma_rate(int mode, int rows, int depth, int iters, int boxes_total, const void* buffer, int ctas,
+                        float* bytes_per_clk, float* us_per_iter);
+
 #ifdef __cplusplus
 }
 #endif

@@ -256,8 +256,13 @@ act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restr
 // time) and, when pf_self is set (first layer of a stack), its own.  After the wait up to 64 K rows / 64 V rows are in flight.
 constexpr int AF_MAXT = 512;
 
+// rows [0, t) of one (b, head) are t * 128 contiguous bytes: one bulk L2 prefetch per 16 KB
 __device__ __forceinline__ void af_prefetch_rows(const h16* base, int t, int lane) {
-    for (int j = lane; j < t; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)j * 64));
+    const int chunks = (t + 127) >> 7;
+    if (lane < chunks) {
+        const int rows = (t - lane * 128) < 128 ? (t - lane * 128) : 128;
+        tc::bulk_prefetch_l2(base + (int64_t)lane * 128 * 64, (uint32_t)rows * 128u);
+    }
 }
 // pv[u] = this lane's partial dot product for key u (u < 32); returns the full dot product of key `lane`
 __device__ __forceinline__ float af_transpose_reduce(float (&pv)[32], int lane) {
@@ -346,6 +351,7 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
         }
     }
     m = warp_max(m);
+    if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[2] = tc::gtimer();      // scores done
     float sum = 0.f;
     for (int j = lane; j < t; j += 32) {
         float e = __expf(ps[j] - m);
@@ -372,7 +378,7 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     }
     *reinterpret_cast<uint32_t*>(att + (int64_t)b * E + c) = pack_h16x2(o.x * inv, o.y * inv, bf);
     }
-    TR_OUT(tr);
+    if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[3] = tc::gtimer();
 }
 
 // Causal attention over a whole prefix in one launch (batched prefill / teacher-forced forward).  qkv [M, 3E] 16-bit (bias already

@@ -21,8 +21,10 @@
 namespace rqb {
 
 struct ConvTcParams {
-    int B, H, W, Cin, Cout;        // H,W: output == input extent (stride 1, "same" padding)
+    int B, H, W, Cin, Cout;        // H,W: OUTPUT extent; the input is H*stride x W*stride
     int ks;                        // 1 or 3
+    int stride;                    // 1: "same" zero padding; 2: no left/top pad, one zero column/row on the right/bottom (F.pad
+                                   // (0,1,0,1) + stride-2 conv, layers.py:50-57) -- both are the tensor map's out-of-bounds fill
     int TW, TH, NB;                // tile box, TW*TH*NB == 128
     int tiles_x, tiles_y, tiles_b, n_tiles_n;
     const float* bias;
@@ -57,7 +59,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cslabs = p.Cin / 64;
     const int nkb = p.ks * p.ks * cslabs;
-    const int pad = p.ks == 3 ? 1 : 0;
+    const int pad = (p.ks == 3 && p.stride == 1) ? 1 : 0;
+    const int sx = p.stride;
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
     const int total = m_tiles * p.n_tiles_n;
 
@@ -88,10 +91,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int ky = tap / p.ks, kx = tap % p.ks;
                     tc::mbar_expect_tx(&full[s], STAGE_BYTES);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    tc::tma_load_4d(st, &tmA, &full[s], c0, x0 + kx - pad, y0 + ky - pad, b0, tc::L2_EVICT_NORMAL);
+                    tc::tma_load_4d(st, &tmA, &full[s], c0, x0 * sx + kx - pad, y0 * sx + ky - pad, b0, tc::L2_EVICT_NORMAL);
                     tc::tma_load_2d(st + OFF_B, &tmB, &full[s], tap * p.Cin + c0, nt * BN, tc::L2_EVICT_LAST);
                     if (PASSES == 3) {
-                        tc::tma_load_4d(st + CT_A_BYTES, &tmAlo, &full[s], c0, x0 + kx - pad, y0 + ky - pad, b0, tc::L2_EVICT_NORMAL);
+                        tc::tma_load_4d(st + CT_A_BYTES, &tmAlo, &full[s], c0, x0 * sx + kx - pad, y0 * sx + ky - pad, b0, tc::L2_EVICT_NORMAL);
                         tc::tma_load_2d(st + OFF_B + B_BYTES, &tmBlo, &full[s], tap * p.Cin + c0, nt * BN, tc::L2_EVICT_LAST);
                     }
                 }
@@ -208,19 +211,20 @@ static int sm_count() {
 }
 
 bool conv_tc_supported(int H, int W, int Cin, int Cout, int ks, int stride, int in_nchw) {
-    if (stride != 1 || in_nchw || (ks != 1 && ks != 3)) return false;
+    if ((stride != 1 && !(stride == 2 && ks == 3)) || in_nchw || (ks != 1 && ks != 3)) return false;
     if (Cin % 64 != 0) return false;
     if (Cout != 3 && Cout % 128 != 0 && Cout != 64) return false;     // bias/residual float4 path needs Cout % 16 == 0
     auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
     return pow2(H) && pow2(W);
 }
 
-// X: NHWC fp16 [B,H,W,Cin]; Wt: [Cout, ks, ks, Cin] fp16; out fp32.  X16lo/W16lo non-null -> split-fp16 (3 products).
+// X: NHWC fp16 [B,H*stride,W*stride,Cin]; Wt: [Cout, ks, ks, Cin] fp16; out fp32 [B,H,W,Cout].  X16lo/W16lo non-null -> split-fp16
+// (3 products).  H, W are the OUTPUT extent.
 int launch_conv_tc(const void* X16, const void* W16, const void* X16lo, const void* W16lo, const float* bias,
                    const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ks, int out_nchw,
-                   cudaStream_t st) {
+                   cudaStream_t st, int stride) {
     ConvTcParams p = {};
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ks;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ks; p.stride = stride;
     p.TW = W < 16 ? W : 16;
     p.TH = (128 / p.TW) < H ? (128 / p.TW) : H;
     p.NB = 128 / (p.TW * p.TH);
@@ -230,14 +234,14 @@ int launch_conv_tc(const void* X16, const void* W16, const void* X16lo, const vo
     p.n_tiles_n = (int)ceil_div(Cout, BN);
     p.bias = bias; p.residual = residual; p.out = out; p.out_nchw = out_nchw;
     CUtensorMap tmA, tmB;
-    RQB_TRY(make_tmap_4d_nhwc(&tmA, X16, (uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B, 64, (uint32_t)p.TW, (uint32_t)p.TH,
-                              (uint32_t)p.NB));
+    RQB_TRY(make_tmap_4d_nhwc(&tmA, X16, (uint64_t)Cin, (uint64_t)W * stride, (uint64_t)H * stride, (uint64_t)B, 64, (uint32_t)p.TW,
+                              (uint32_t)p.TH, (uint32_t)p.NB, (uint32_t)stride));
     RQB_TRY(make_tmap_2d(&tmB, W16, 1, (uint64_t)ks * ks * Cin, (uint64_t)Cout, (uint64_t)ks * ks * Cin * 2, 64, (uint32_t)BN));
     const int n_sm = sm_count();
     if (X16lo != nullptr && W16lo != nullptr) {
         CUtensorMap tmAlo, tmBlo;
-        RQB_TRY(make_tmap_4d_nhwc(&tmAlo, X16lo, (uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B, 64, (uint32_t)p.TW,
-                                  (uint32_t)p.TH, (uint32_t)p.NB));
+        RQB_TRY(make_tmap_4d_nhwc(&tmAlo, X16lo, (uint64_t)Cin, (uint64_t)W * stride, (uint64_t)H * stride, (uint64_t)B, 64,
+                                  (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.NB, (uint32_t)stride));
         RQB_TRY(make_tmap_2d(&tmBlo, W16lo, 1, (uint64_t)ks * ks * Cin, (uint64_t)Cout, (uint64_t)ks * ks * Cin * 2, 64, (uint32_t)BN));
         switch (BN) {
             case 16: return launch_conv_tc_t<16, 5, 3>(tmA, tmB, tmAlo, tmBlo, p, n_sm, st);
@@ -377,9 +381,12 @@ int launch_cast_f16(const float* X, void* Y16, void* Y16lo, int B, int H, int W,
 }  // namespace rqb
 
 // diagnostic entry point: one conv through the tcgen05 path (tests/test_gpu_tc.py)
+// out_nchw bit 0: NCHW output; bits 8.. : stride (0/1 -> 1, 2 -> the Downsample conv; then H, W are the OUTPUT extent)
 extern "C" int rqb200_dbg_conv_tc(const void* X16, const void* W16, const void* X16lo, const void* W16lo, const float* bias,
                                   const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ks, int out_nchw,
                                   void* stream) {
-    if (!rqb::conv_tc_supported(H, W, Cin, Cout, ks, 1, 0)) return rqb::fail(RQB200_EINVAL, "conv_tc: unsupported shape");
-    return rqb::launch_conv_tc(X16, W16, X16lo, W16lo, bias, residual, out, B, H, W, Cin, Cout, ks, out_nchw, (cudaStream_t)stream);
+    const int stride = (out_nchw >> 8) > 1 ? (out_nchw >> 8) : 1;
+    if (!rqb::conv_tc_supported(H, W, Cin, Cout, ks, stride, 0)) return rqb::fail(RQB200_EINVAL, "conv_tc: unsupported shape");
+    return rqb::launch_conv_tc(X16, W16, X16lo, W16lo, bias, residual, out, B, H, W, Cin, Cout, ks, out_nchw & 1, (cudaStream_t)stream,
+                               stride);
 }

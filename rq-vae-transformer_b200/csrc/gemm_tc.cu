@@ -57,14 +57,16 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes_log2, uint64
     return 0;
 }
 
+// stride > 1: the box samples every `stride`-th pixel along W and H (a strided conv's input pixels for one filter tap): boxDim is
+// the traversed extent, the unit loads boxDim / elementStride elements
 int make_tmap_4d_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_c,
-                      uint32_t box_w, uint32_t box_h, uint32_t box_b) {
+                      uint32_t box_w, uint32_t box_h, uint32_t box_b, uint32_t stride) {
     PFN_cuTensorMapEncodeTiled_v12000 enc;
     RQB_TRY(get_encode_fn(&enc));
     cuuint64_t dims[4] = {C, W, H, B};
     cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-    cuuint32_t box[4] = {box_c, box_w, box_h, box_b};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {box_c, box_w * stride, box_h * stride, box_b};
+    cuuint32_t estr[4] = {1, stride, stride, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

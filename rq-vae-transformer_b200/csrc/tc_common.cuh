@@ -142,6 +142,6 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int ab_format) {
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes_log2 /*1 = 16-bit*/, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 int make_tmap_4d_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_c,
-                      uint32_t box_w, uint32_t box_h, uint32_t box_b);
+                      uint32_t box_w, uint32_t box_h, uint32_t box_b, uint32_t stride);
 
 }  // namespace rqb

@@ -46,7 +46,7 @@ struct VaeRun {
 
     // ---- fast tier helpers (tcgen05 implicit GEMM; decoder only, C % 128 == 0 everywhere)
     int conv_f(const std::string& name, const __half* in16, float* out, const float* resid, int Hh, int Ww, int Cin, int Cout,
-               int ks, int out_nchw) {
+               int ks, int out_nchw, int stride = 1) {
         const VTensor* w = get(name + ".weight", (int64_t)Cout * ks * ks * Cin);
         const VTensor* b = get(name + ".bias", Cout);
         note_act((int64_t)Hh * Ww, Cout);
@@ -60,7 +60,7 @@ struct VaeRun {
             w_lo = wl->ptr;
             in_lo = in16 == h16[0] ? l16[0] : l16[1];
         }
-        return launch_conv_tc(in16, w->ptr, in_lo, w_lo, (const float*)b->ptr, resid, out, B, Hh, Ww, Cin, Cout, ks, out_nchw, st);
+        return launch_conv_tc(in16, w->ptr, in_lo, w_lo, (const float*)b->ptr, resid, out, B, Hh, Ww, Cin, Cout, ks, out_nchw, st, stride);
     }
     int gn_f(const std::string& name, const float* in, __half* out16, int HW, int C, int silu) {
         const VTensor* g = get(name + ".weight", C);
@@ -224,9 +224,9 @@ struct VaeRun {
         return conv("decoder.conv_out", buf[a], out, nullptr, res, res, ch, c.out_ch, 3, 1, 0, 0, 1);
     }
 
-    // fast-tier encoder (experiment, RQB200_ENC_FAST=1 on the host side registers fp16 hi/lo weights for these layers): every
-    // stride-1 conv on the tcgen05 path through the decoder's building blocks; conv_in (Cin = 3, NCHW input) and the five
-    // stride-2 downsample convs stay on the fp32 FFMA kernel (2 % of the encoder's flops)
+    // fast-tier encoder: every conv but conv_in on the tcgen05 path through the decoder's building blocks, the five stride-2
+    // Downsample convs included (tensor map with element stride 2); conv_in (Cin = 3, NCHW fp32 input, 0.3 % of the encoder's
+    // flops) stays on the fp32 FFMA kernel
     int encode_fast(const float* x, float* z_e) {
         const rqb200_vae_config& c = h->cfg;
         const int nl = c.n_levels, nb = c.num_res_blocks;
@@ -242,7 +242,10 @@ struct VaeRun {
             }
             if (lvl != nl - 1) {
                 int nxt = (cur + 1) & 3;
-                rc = conv(p + ".downsample.conv", buf[cur], buf[nxt], nullptr, res, res, ch, ch, 3, 2, 0, 0, 0); if (rc) return rc;
+                // Downsample (layers.py:50-57): pad (0,1,0,1) + 3x3 stride 2 = the same implicit GEMM through a tensor map that
+                // samples every other pixel; the one-pixel right/bottom pad is its out-of-bounds fill
+                if (!dry) { rc = launch_cast_f16(buf[cur], h16[1], l16[1], B, res, res, ch, 0, st); if (rc) return rc; }
+                rc = conv_f(p + ".downsample.conv", h16[1], buf[nxt], nullptr, res / 2, res / 2, ch, ch, 3, 0, 2); if (rc) return rc;
                 cur = nxt;
                 res /= 2;
             }

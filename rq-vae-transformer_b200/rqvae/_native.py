@@ -67,6 +67,8 @@ def lib():
     L.rqb200_rq_embed_depth.argtypes = L.rqb200_rq_embed_sum.argtypes
     L.rqb200_sample_logits.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p,
                                        C.c_void_p]
+    L.rqb200_dbg_tma_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float)]
     L.rqb200_dbg_rq_quantize.argtypes = [C.c_int] + L.rqb200_rq_quantize.argtypes
     L.rqb200_dbg_sample_logits.argtypes = [C.c_int] + L.rqb200_sample_logits.argtypes
     L.rqb200_ar_create.restype = C.c_void_p
@@ -117,7 +119,7 @@ EXPORTS = ["rqb200_last_error", "rqb200_version", "rqb200_device_count", "rqb200
            "rqb200_vae_destroy", "rqb200_vae_set_tensor", "rqb200_vae_finalize", "rqb200_vae_workspace_bytes",
            "rqb200_vae_decode", "rqb200_vae_decode_code", "rqb200_vae_encode", "rqb200_vae_last_launches",
            "rqb200_dbg_gemm_tc", "rqb200_dbg_conv_tc", "rqb200_dbg_chain", "rqb200_dbg_rq_quantize",
-           "rqb200_dbg_sample_logits"]
+           "rqb200_dbg_sample_logits", "rqb200_dbg_tma_rate"]
 
 
 def check(rc, what=""):

@@ -91,7 +91,9 @@ class RQVAE(Stage1Model):
         if not handle:
             raise N.NativeError("rqb200_vae_create: " + L.rqb200_last_error().decode())
         wdt = torch.float16 if mode == N.MODE_FAST else torch.float32
-        enc_fast = mode == N.MODE_FAST and os.environ.get("RQB200_ENC_FAST", "0") == "1"
+        # fast tier: the encoder runs on the tcgen05 conv path as well (every conv but the Cin = 3 conv_in); RQB200_ENC_FAST=0 keeps
+        # the encoder on the fp32 kernels
+        enc_fast = mode == N.MODE_FAST and os.environ.get("RQB200_ENC_FAST", "1") == "1"
         keep = {}
 
         def reg(name, t):
@@ -103,9 +105,8 @@ class RQVAE(Stage1Model):
             """conv weight OIHW -> OHWI in the engine's dtype; fast tier: fp16 hi + lo halves (split-fp16 products)"""
             w = w_oihw.detach().permute(0, 2, 3, 1).contiguous().float()
             fast16 = name.startswith(("decoder.", "post_quant_conv"))
-            if enc_fast and name.startswith(("encoder.", "quant_conv")) and not name.startswith("encoder.conv_in") \
-                    and ".downsample." not in name:
-                fast16 = True     # experiment (RQB200_ENC_FAST=1): the encoder's stride-1 convs on the tcgen05 path too
+            if enc_fast and name.startswith(("encoder.", "quant_conv")) and not name.startswith("encoder.conv_in"):
+                fast16 = True
             if mode == N.MODE_FAST and fast16:
                 hi = w.to(torch.float16)
                 reg(name, hi)

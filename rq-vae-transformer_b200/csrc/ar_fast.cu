@@ -296,17 +296,29 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     h16* kb = kc + pair;
     h16* vb = vc + pair;
     int t = 0;
+    uint32_t kr[64];                               // K rows [0, min(t, 64)) of this (b, head): lane <-> 2 dims
     if (early_t) {
         // (position counters are only advanced by the LAST kernel of a graph; no kernel upstream of this one in the graph writes them)
         t = t_ptr ? *reinterpret_cast<const volatile int*>(t_ptr) : t_host;
         if (valid) {
-            if (pf_self) { af_prefetch_rows(kb, t, lane); af_prefetch_rows(vb, t, lane); }
+            if (pf_self) { af_prefetch_rows(vb, t, lane); if (t > 64) af_prefetch_rows(kb, t, lane); }
             if (kc_pf) { af_prefetch_rows(kc_pf + pair, t, lane); af_prefetch_rows(vc_pf + pair, t, lane); }
+            // the first 64 cached K rows go straight into registers: their round trip overlaps the wait for the qkv GEMM
+#pragma unroll
+            for (int u = 0; u < 64; u++)
+                kr[u] = (u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)u * 64 + 2 * lane) : 0u;
         }
     }
     tc::pdl_wait();
     TR_DEP(tr);
-    if (!early_t) t = t_ptr ? *t_ptr : t_host;
+    if (!early_t) {
+        t = t_ptr ? *t_ptr : t_host;
+        if (valid) {
+#pragma unroll
+            for (int u = 0; u < 64; u++)
+                kr[u] = (u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)u * 64 + 2 * lane) : 0u;
+        }
+    }
     if (valid) {
     const int c = h * 64 + 2 * lane;
     float2 q = make_float2(bqkv[c], bqkv[c + 1]);
@@ -327,11 +339,12 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     const float2 qf = unpack_h16x2(pack_h16x2(q.x, q.y, bf), bf), kf = unpack_h16x2(k2, bf), vf = unpack_h16x2(v2, bf);
     const float s_new = warp_sum(qf.x * kf.x + qf.y * kf.y) * 0.125f;
     float m = s_new;
-    for (int j0 = 0; j0 < t; j0 += 64) {          // scores of the cached rows: 64 coalesced row reads in flight
-        uint32_t kr[64];
+    for (int j0 = 0; j0 < t; j0 += 64) {          // scores of the cached rows, 64 at a time
+        if (j0 > 0) {                              // (T > 64 only: the later rows are fetched here)
 #pragma unroll
-        for (int u = 0; u < 64; u++)
-            kr[u] = (j0 + u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)(j0 + u) * 64 + 2 * lane) : 0u;
+            for (int u = 0; u < 64; u++)
+                kr[u] = (j0 + u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)(j0 + u) * 64 + 2 * lane) : 0u;
+        }
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             if (j0 + half * 32 < t) {                                  // (warp-uniform)
@@ -350,6 +363,11 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
             }
         }
     }
+    // the V rows do not depend on the scores: the first 64 are requested before the softmax arithmetic
+    uint32_t raw[64];
+#pragma unroll
+    for (int u = 0; u < 64; u++)
+        raw[u] = (u < t) ? *reinterpret_cast<const uint32_t*>(vb + (int64_t)u * 64 + 2 * lane) : 0u;
     m = warp_max(m);
     if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[2] = tc::gtimer();      // scores done
     float sum = 0.f;
@@ -363,11 +381,12 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     __syncwarp();
     const float inv = 1.0f / sum;
     float2 o = make_float2(e_new * vf.x, e_new * vf.y);
-    for (int j0 = 0; j0 < t; j0 += 64) {                  // up to 64 V rows in flight (rows added in cache order)
-        uint32_t raw[64];
+    for (int j0 = 0; j0 < t; j0 += 64) {                  // (rows added in cache order)
+        if (j0 > 0) {
 #pragma unroll
-        for (int u = 0; u < 64; u++)
-            raw[u] = (j0 + u < t) ? *reinterpret_cast<const uint32_t*>(vb + (int64_t)(j0 + u) * 64 + 2 * lane) : 0u;
+            for (int u = 0; u < 64; u++)
+                raw[u] = (j0 + u < t) ? *reinterpret_cast<const uint32_t*>(vb + (int64_t)(j0 + u) * 64 + 2 * lane) : 0u;
+        }
 #pragma unroll
         for (int u = 0; u < 64; u++)
             if (j0 + u < t) {
@@ -532,7 +551,7 @@ struct ArFast {
     cudaGraphExec_t graphs[G_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     int64_t n_nodes[G_COUNT] = {0, 0, 0, 0};   // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
-    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, next_pf = true, ln_cluster = false, kv_pf = true;
+    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, next_pf = true, ln_cluster = false, kv_pf = true, batched_deep = false;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
     int n_sm = 148;
     // diagnostic stage trace (cfg.flags & RQB200_AR_TRACE)
@@ -808,6 +827,7 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     f->next_pf = !(cfg.flags & RQB200_AR_NO_NEXT_PREFETCH);
     f->ln_cluster = (cfg.flags & RQB200_AR_LN_CLUSTER) != 0;
     f->kv_pf = !(cfg.flags & RQB200_AR_NO_KV_PREFETCH);
+    f->batched_deep = (cfg.flags & RQB200_AR_BATCHED_DEEP_RING) != 0;
     {
         int dev = 0, n = 0;
         cudaGetDevice(&dev);
@@ -868,6 +888,10 @@ static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blo
     RQB_TRY(make_tmap_2d(&tx_h, bb.H, 1, 4 * E, M, (uint64_t)E * 8, 64, bn));
     RQB_ENSURE_SMEM(prefill_attn_smem(PA_MAXT), prefill_attn_kernel);
     const float* nof = nullptr;
+    // large-M launches: half-depth rings put two CTAs on an SM, so one tile's epilogue overlaps the other's main loop
+    const bool save_deep = f.deep;
+    if (M > 256 && !f.batched_deep) f.deep = false;
+    struct Restore { ArFast& f; bool d; ~Restore() { f.deep = d; } } restore{f, save_deep};
     for (size_t l = 0; l < blocks.size(); l++) {
         const rqb200_block_weights& bw = blocks[l];
         RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, bw.ln1_w, bw.ln1_b, bb.XN, st));

@@ -48,6 +48,7 @@ extern "C" {
 #define RQB200_AR_NO_NEXT_PREFETCH 64   /* fc1 does not pull fc2's weights into L2                                          */
 #define RQB200_AR_NO_KV_PREFETCH 256    /* attention does not pull the next layer's cache rows into L2 ahead of time          */
 #define RQB200_AR_BATCHED_DEEP_RING 512 /* large-M passes (prefill / forward) keep the deep ring: one CTA per SM                  */
+#define RQB200_AR_BATCHED_STREAMER 1024 /* large-M passes through the weight-streaming GEMM instead of the persistent rows GEMM    */
 #define RQB200_AR_LN_CLUSTER 128        /* reduction + LayerNorm rows split over 2-CTA clusters (DSMEM statistics exchange)  */
 
 const char* rqb200_last_error(void);
@@ -219,6 +220,11 @@ int rqb200_dbg_conv_tc(const void* X16, const void* W16, const void* X16lo, cons
 int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, int smem_bytes, int fan, int reps, void* workspace,
                      size_t workspace_bytes, float* us_per_stage);
 
+/* rqb200_dbg_rows_gemm: the large-M GEMM of the batched prefill / forward passes (csrc/conv_tc.cu launch_rows_gemm_tc: persistent
+ * 128 x BN tiles, double-buffered TMEM): out[m,n] = act(sum_k X[m,k] W[n,k] + bias[n]) (+ residual[m,n]).  X [ceil(M/128)*128, K] and
+ * W [N_out,K] 16-bit (fmt 0 fp16 / 1 bf16); exactly one of out_f32 / out_16; gelu applies to out_16 only. */
+int rqb200_dbg_rows_gemm(const void* X16, const void* W16, const float* bias, const float* residual, float* out_f32, void* out_16,
+                         int gelu, int fmt, int64_t M, int N_out, int K, void* stream);
 /* rqb200_dbg_tma_rate: micro-benchmark of one SM's shared-memory fill rate from L2 (csrc/dbg_tma.cu).  mode 0: tensor-map boxes
  * of `rows` x 128 B (what the GEMM kernels issue); mode 1: 1-D bulk copies of rows*128 contiguous bytes.  `depth` loads in flight,
  * `iters` rounds, every CTA cycling over the same `boxes_total` boxes of `buffer` (>= boxes_total*rows*128 bytes). */

@@ -551,7 +551,7 @@ struct ArFast {
     cudaGraphExec_t graphs[G_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     int64_t n_nodes[G_COUNT] = {0, 0, 0, 0};   // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
-    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, next_pf = true, ln_cluster = false, kv_pf = true, batched_deep = false;
+    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, next_pf = true, ln_cluster = false, kv_pf = true, batched_deep = false, batched_streamer = false;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
     int n_sm = 148;
     // diagnostic stage trace (cfg.flags & RQB200_AR_TRACE)
@@ -614,11 +614,12 @@ static size_t fast_layout(const ArFast& f, int B, void* base, size_t cap, FastWs
     w.kc_head = a.take<h16>(per_head * c.n_head_layers);
     w.vc_head = a.take<h16>(per_head * c.n_head_layers);
     w.Mmax = f.batched_prefill ? (int64_t)B * prefill_tmax(c) : 0;
-    w.PX = a.take<float>(w.Mmax * E);
-    w.PXN = a.take<h16>(w.Mmax * E);
-    w.PQKV = a.take<h16>(w.Mmax * 3 * E);
-    w.PATT = a.take<h16>(w.Mmax * E);
-    w.PH = a.take<h16>(w.Mmax * 4 * E);
+    const int64_t Mp = w.Mmax ? w.Mmax + 128 : 0;          // (the rows GEMM reads whole 128-row tiles)
+    w.PX = a.take<float>(Mp * E);
+    w.PXN = a.take<h16>(Mp * E);
+    w.PQKV = a.take<h16>(Mp * 3 * E);
+    w.PATT = a.take<h16>(Mp * E);
+    w.PH = a.take<h16>(Mp * 4 * E);
     w.PS = a.take<h16>(w.Mmax * c.code_dim);
     if (ws) *ws = w;
     return a.off + 256;
@@ -828,6 +829,7 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     f->ln_cluster = (cfg.flags & RQB200_AR_LN_CLUSTER) != 0;
     f->kv_pf = !(cfg.flags & RQB200_AR_NO_KV_PREFETCH);
     f->batched_deep = (cfg.flags & RQB200_AR_BATCHED_DEEP_RING) != 0;
+    f->batched_streamer = (cfg.flags & RQB200_AR_BATCHED_STREAMER) != 0;
     {
         int dev = 0, n = 0;
         cudaGetDevice(&dev);
@@ -892,10 +894,15 @@ static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blo
     const bool save_deep = f.deep;
     if (M > 256 && !f.batched_deep) f.deep = false;
     struct Restore { ArFast& f; bool d; ~Restore() { f.deep = d; } } restore{f, save_deep};
+    // M > 256: the persistent rows GEMM (conv_tc.cu: 128 x 256 tiles, double-buffered TMEM, epilogue overlapped with the next
+    // tile); M <= 256: the weight streamer
+    const bool rows = M > 256 && !f.batched_streamer;
     for (size_t l = 0; l < blocks.size(); l++) {
         const rqb200_block_weights& bw = blocks[l];
         RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, bw.ln1_w, bw.ln1_b, bb.XN, st));
-        {
+        if (rows) {
+            RQB_TRY(launch_rows_gemm_tc(bb.XN, bw.wqkv, bw.bqkv, nullptr, nullptr, bb.QKV, 0, f.bf, M, 3 * E, E, st));
+        } else {
             GemmTcParams p = gemm_base(f, 3 * E, E, (int)M, 1, GT_H16);
             p.bias = bw.bqkv; p.out = bb.QKV;
             RQB_TRY(launch_gemm_tc(maps[l].qkv, tx_xn, p, pdl, st));
@@ -903,21 +910,28 @@ static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blo
         RQB_TRY(launch_pdl(prefill_attn_kernel, dim3((unsigned)(G * c.n_head)), dim3(128), prefill_attn_smem(T), st, pdl,
                            (const h16*)bb.QKV, kc ? kc + kv_per_layer * l : nullptr, vc ? vc + kv_per_layer * l : nullptr, bb.ATT, G, T, E,
                            c.n_head, Tmax, f.bf));
-        {
+        if (rows) {
+            RQB_TRY(launch_rows_gemm_tc(bb.ATT, bw.wproj, bw.bproj, bb.X, bb.X, nullptr, 0, f.bf, M, E, E, st));
+        } else {
             GemmTcParams p = gemm_base(f, E, E, (int)M, 1, GT_F32);
             p.bias = bw.bproj; p.out = bb.X; p.residual = bb.X; p.ld_res = E;
             RQB_TRY(launch_gemm_tc(maps[l].proj, tx_att, p, pdl, st));
         }
         RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, bw.ln2_w, bw.ln2_b, bb.XN, st));
-        {
-            GemmTcParams p = gemm_base(f, 4 * E, E, (int)M, 1, GT_H16_GELU);
-            p.bias = bw.b1; p.out = bb.H;
-            RQB_TRY(launch_gemm_tc(maps[l].fc1, tx_xn, p, pdl, st));
-        }
-        {
-            GemmTcParams p = gemm_base(f, E, 4 * E, (int)M, 1, GT_F32);
-            p.bias = bw.b2; p.out = bb.X; p.residual = bb.X; p.ld_res = E;
-            RQB_TRY(launch_gemm_tc(maps[l].fc2, tx_h, p, pdl, st));
+        if (rows) {
+            RQB_TRY(launch_rows_gemm_tc(bb.XN, bw.w1, bw.b1, nullptr, nullptr, bb.H, 1, f.bf, M, 4 * E, E, st));
+            RQB_TRY(launch_rows_gemm_tc(bb.H, bw.w2, bw.b2, bb.X, bb.X, nullptr, 0, f.bf, M, E, 4 * E, st));
+        } else {
+            {
+                GemmTcParams p = gemm_base(f, 4 * E, E, (int)M, 1, GT_H16_GELU);
+                p.bias = bw.b1; p.out = bb.H;
+                RQB_TRY(launch_gemm_tc(maps[l].fc1, tx_xn, p, pdl, st));
+            }
+            {
+                GemmTcParams p = gemm_base(f, E, 4 * E, (int)M, 1, GT_F32);
+                p.bias = bw.b2; p.out = bb.X; p.residual = bb.X; p.ld_res = E;
+                RQB_TRY(launch_gemm_tc(maps[l].fc2, tx_h, p, pdl, st));
+            }
         }
     }
     return 0;
@@ -983,7 +997,7 @@ static size_t forward_layout(const ArFast& f, int B, void* base, size_t cap, Fwd
     const rqb200_ar_config& c = f.cfg;
     Arena a(base, cap);
     const int64_t E = c.embed_dim, HW = (int64_t)c.H * c.W, Tb = c.cond_len + HW - 1;
-    const int64_t Mb = B * Tb, Mh = (int64_t)c.D * HW * B, Mm = std::max(Mb, Mh);
+    const int64_t Mb = B * Tb, Mh = (int64_t)c.D * HW * B, Mm = std::max(Mb, Mh) + 128;   // (+128: whole-tile reads of the rows GEMM)
     FwdWs w;
     w.state = a.take<StepState>(1);
     w.BX = a.take<float>(Mb * E);
@@ -1048,9 +1062,13 @@ int ar_fast_forward(ArFast* f, const int64_t* codes, const int64_t* cond, int B,
         CUtensorMap tx;
         RQB_TRY(make_tmap_2d(&tx, ws.XN, 1, E, Mh, (uint64_t)E * 2, 64, gemm_tc_bn((int)std::min<int64_t>(Mh, 256))));
         RQB_TRY(ln(*f, "", (int)Mh, ws.HX, nof, 0, nof, nof, nullptr, w.cls_ln_w, w.cls_ln_b, ws.XN, st));
-        GemmTcParams p = gemm_base(*f, V, E, (int)Mh, 1, GT_F32);
-        p.bias = w.b_cls; p.out = logits_out;
-        RQB_TRY(launch_gemm_tc(f->tm_cls, tx, p, false, st));
+        if (Mh > 256 && !f->batched_streamer) {
+            RQB_TRY(launch_rows_gemm_tc(ws.XN, w.w_cls, w.b_cls, nullptr, logits_out, nullptr, 0, f->bf, Mh, V, E, st));
+        } else {
+            GemmTcParams p = gemm_base(*f, V, E, (int)Mh, 1, GT_F32);
+            p.bias = w.b_cls; p.out = logits_out;
+            RQB_TRY(launch_gemm_tc(f->tm_cls, tx, p, false, st));
+        }
         return 0;
     }();
     f->use_pdl = save_pdl;

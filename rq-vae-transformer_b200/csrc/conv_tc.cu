@@ -31,6 +31,10 @@ struct ConvTcParams {
     const float* residual;         // [B,H,W,Cout] f32 or null
     float* out;                    // NHWC f32, or NCHW f32 when out_nchw
     int out_nchw;
+    // "rows GEMM" use of the same kernel (launch_rows_gemm_tc: a 1x1 conv over M token rows viewed as 16x8-pixel images):
+    void* out16;                   // non-null: 16-bit NHWC output (fmt) instead of `out`, optionally through GELU
+    int gelu, fmt;                 // fmt: 16-bit operand / output format, 0 fp16 (all convs), 1 bf16
+    int64_t m_rows;                // > 0: only pixels (rows) below m_rows are stored
 };
 
 constexpr int CT_THREADS = 192;
@@ -101,7 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = tc::umma_idesc(128, BN, 0 /*fp16*/);
+        const uint32_t idesc = tc::umma_idesc(128, BN, p.fmt);
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, tcount++) {
             const uint32_t as = tcount & 1;
@@ -143,8 +147,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
             const int x = tx * p.TW + rx, y = ty * p.TH + ry, b = tb * p.NB + rb;
-            const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
             const int64_t pix = ((int64_t)b * p.H + y) * p.W + x;
+            const bool valid = (x < p.W) && (y < p.H) && (b < p.B) && (p.m_rows == 0 || pix < p.m_rows);
             tc::mbar_wait(&tfull[as], (tcount >> 1) & 1);
             tc::tc_fence_after();
 #pragma unroll 1
@@ -161,6 +165,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (n < p.Cout)
                             p.out[(((int64_t)b * p.Cout + n) * p.H + y) * p.W + x] = __uint_as_float(v[i]) + p.bias[n];
                     }
+                } else if (p.out16 != nullptr) {
+                    float w[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + i);
+                        w[i] = __uint_as_float(v[i]) + bb.x; w[i + 1] = __uint_as_float(v[i + 1]) + bb.y;
+                        w[i + 2] = __uint_as_float(v[i + 2]) + bb.z; w[i + 3] = __uint_as_float(v[i + 3]) + bb.w;
+                    }
+                    if (p.gelu) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) w[i] = 0.5f * w[i] * (1.0f + erff(w[i] * 0.70710678118654752440f));
+                    }
+                    uint4 pk[2];
+                    uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) pw[i] = pack_h16x2(w[2 * i], w[2 * i + 1], p.fmt);
+                    uint4* o16 = reinterpret_cast<uint4*>(reinterpret_cast<h16*>(p.out16) + pix * p.Cout + n0);
+                    o16[0] = pk[0];
+                    o16[1] = pk[1];
                 } else {
                     float* o = p.out + pix * p.Cout + n0;
                     const float* rs = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
@@ -256,6 +279,32 @@ int launch_conv_tc(const void* X16, const void* W16, const void* X16lo, const vo
         case 128: return launch_conv_tc_t<128, 6, 1>(tmA, tmB, tmA, tmB, p, n_sm, st);
         default: return launch_conv_tc_t<256, 4, 1>(tmA, tmB, tmA, tmB, p, n_sm, st);
     }
+}
+
+// Rows GEMM through the persistent conv kernel: out[m, n] = act(sum_k X[m,k] W[n,k] + bias[n]) (+ residual[m,n]) for M token rows
+// -- a 1x1 "conv" over ceil(M/128) images of 16x8 pixels.  The batched prefill / teacher-forced forward passes of the AR tier
+// (csrc/ar_fast.cu) use it for M > 256: persistent CTAs, 128 x BN tiles, double-buffered TMEM accumulators whose epilogue
+// overlaps the next tile's main loop -- what gemm_tc_kernel (a weight streamer built for M <= 256) does not have.
+// X [M_alloc, K] 16-bit with M_alloc >= ceil(M/128)*128 rows readable; exactly one of out_f32 / out_16 non-null;
+// residual (f32, may alias out_f32) only with out_f32.  N_out % 128 == 0, K % 64 == 0.
+int launch_rows_gemm_tc(const void* X16, const void* W16, const float* bias, const float* residual, float* out_f32, void* out_16,
+                        int gelu, int fmt, int64_t M, int N_out, int K, cudaStream_t st) {
+    if (N_out % 128 != 0 || K % 64 != 0 || M < 1 || (out_f32 == nullptr) == (out_16 == nullptr) || bias == nullptr)
+        return fail(RQB200_EINVAL, "rows_gemm_tc: need N_out % 128 == 0, K % 64 == 0, a bias and exactly one output");
+    ConvTcParams p = {};
+    p.B = (int)ceil_div(M, 128); p.H = 8; p.W = 16; p.Cin = K; p.Cout = N_out; p.ks = 1; p.stride = 1;
+    p.TW = 16; p.TH = 8; p.NB = 1;
+    p.tiles_x = 1; p.tiles_y = 1; p.tiles_b = p.B;
+    const int BN = N_out % 256 == 0 ? 256 : 128;
+    p.n_tiles_n = N_out / BN;
+    p.bias = bias; p.residual = residual; p.out = out_f32; p.out_nchw = 0;
+    p.out16 = out_16; p.gelu = gelu; p.fmt = fmt; p.m_rows = M;
+    CUtensorMap tmA, tmB;
+    RQB_TRY(make_tmap_4d_nhwc(&tmA, X16, (uint64_t)K, 16, 8, (uint64_t)p.B, 64, 16, 8, 1, 1));
+    RQB_TRY(make_tmap_2d(&tmB, W16, 1, (uint64_t)K, (uint64_t)N_out, (uint64_t)K * 2, 64, (uint32_t)BN));
+    const int n_sm = sm_count();
+    if (BN == 256) return launch_conv_tc_t<256, 4, 1>(tmA, tmB, tmA, tmB, p, n_sm, st);
+    return launch_conv_tc_t<128, 6, 1>(tmA, tmB, tmA, tmB, p, n_sm, st);
 }
 
 // ------------------------------------------------------------------------------------------------ fp16 operand producers
@@ -389,4 +438,10 @@ extern "C" int rqb200_dbg_conv_tc(const void* X16, const void* W16, const void* 
     if (!rqb::conv_tc_supported(H, W, Cin, Cout, ks, stride, 0)) return rqb::fail(RQB200_EINVAL, "conv_tc: unsupported shape");
     return rqb::launch_conv_tc(X16, W16, X16lo, W16lo, bias, residual, out, B, H, W, Cin, Cout, ks, out_nchw & 1, (cudaStream_t)stream,
                                stride);
+}
+
+// diagnostic entry point: the rows GEMM (tests/test_gpu_tc.py).  X must have ceil(M/128)*128 readable rows.
+extern "C" int rqb200_dbg_rows_gemm(const void* X16, const void* W16, const float* bias, const float* residual, float* out_f32,
+                                    void* out_16, int gelu, int fmt, int64_t M, int N_out, int K, void* stream) {
+    return rqb::launch_rows_gemm_tc(X16, W16, bias, residual, out_f32, out_16, gelu, fmt, M, N_out, K, (cudaStream_t)stream);
 }

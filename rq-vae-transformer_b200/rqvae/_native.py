@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("RQB200_LIB", os.path.join(os.path.dirname(_HERE), "cs
 OK, EINVAL, ECUDA, ENODEV, EWORKSPACE, ESTATE = 0, -1, -2, -3, -4, -5
 F32, BF16, F16 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
-AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_NO_NEXT_PREFETCH, AR_LN_CLUSTER, AR_NO_KV_PREFETCH, AR_BATCHED_DEEP_RING = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_NO_NEXT_PREFETCH, AR_LN_CLUSTER, AR_NO_KV_PREFETCH, AR_BATCHED_DEEP_RING, AR_BATCHED_STREAMER = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 c_f32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p
@@ -67,6 +67,8 @@ def lib():
     L.rqb200_rq_embed_depth.argtypes = L.rqb200_rq_embed_sum.argtypes
     L.rqb200_sample_logits.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p,
                                        C.c_void_p]
+    L.rqb200_dbg_rows_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64,
+                                       C.c_int, C.c_int, C.c_void_p]
     L.rqb200_dbg_tma_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float),
                                       C.POINTER(C.c_float)]
     L.rqb200_dbg_rq_quantize.argtypes = [C.c_int] + L.rqb200_rq_quantize.argtypes
@@ -119,7 +121,7 @@ EXPORTS = ["rqb200_last_error", "rqb200_version", "rqb200_device_count", "rqb200
            "rqb200_vae_destroy", "rqb200_vae_set_tensor", "rqb200_vae_finalize", "rqb200_vae_workspace_bytes",
            "rqb200_vae_decode", "rqb200_vae_decode_code", "rqb200_vae_encode", "rqb200_vae_last_launches",
            "rqb200_dbg_gemm_tc", "rqb200_dbg_conv_tc", "rqb200_dbg_chain", "rqb200_dbg_rq_quantize",
-           "rqb200_dbg_sample_logits", "rqb200_dbg_tma_rate"]
+           "rqb200_dbg_sample_logits", "rqb200_dbg_tma_rate", "rqb200_dbg_rows_gemm"]
 
 
 def check(rc, what=""):
@@ -171,6 +173,7 @@ def ar_engine_options():
     flags |= AR_LN_CLUSTER if env("RQB200_LN_CLUSTER", "0") == "1" else 0
     flags |= AR_NO_KV_PREFETCH if env("RQB200_NO_KV_PF", "0") == "1" else 0
     flags |= AR_BATCHED_DEEP_RING if env("RQB200_BATCHED_DEEP", "0") == "1" else 0
+    flags |= AR_BATCHED_STREAMER if env("RQB200_BATCHED_STREAMER", "0") == "1" else 0
     return {"flags": flags,
             "splits": [int(env("RQB200_SPLIT_" + k, "0")) for k in ("QKV", "PROJ", "FC1", "FC2")]}
 

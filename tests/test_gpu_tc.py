@@ -124,3 +124,30 @@ def test_conv_tc_stride2_downsample(B, Ho, Cin, Cout, split):
                                        B, Ho, Ho, Cin, Cout, 3, 2 << 8, N.stream_ptr()))
     torch.cuda.synchronize()
     torch.testing.assert_close(out.permute(0, 3, 1, 2), ref, rtol=1e-4 if split else 2e-3, atol=1e-4 if split else 2e-3)
+
+
+@pytest.mark.parametrize("M,N_out,K", [(257, 1536, 1536), (2048, 4608, 1536), (1000, 1280, 5120), (4096, 256, 256), (130, 128, 64),
+                                       (6080, 6144, 1536)])
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+def test_rows_gemm_persistent_kernel(M, N_out, K, fmt):
+    """the large-M GEMM of the batched prefill / forward passes (persistent 128 x BN tiles through conv_tc_kernel)"""
+    dt, code = DT[fmt]
+    g = torch.Generator().manual_seed(M + N_out + K)
+    Mp = -(-M // 128) * 128
+    W = (torch.randn(N_out, K, generator=g) / K ** 0.5).to(dt).to(DEV)
+    X = torch.zeros(Mp, K, dtype=dt, device=DEV)
+    X[:M] = torch.randn(M, K, generator=g).to(dt).to(DEV)
+    bias = torch.randn(N_out, generator=g).to(DEV)
+    R = torch.randn(M, N_out, generator=g).to(DEV)
+    ref = X[:M].float() @ W.float().t() + bias
+    L = N.lib()
+    out = torch.cat([R, torch.full((3, N_out), 7.0, device=DEV)])                    # in place + guard rows that must stay untouched
+    N.check(L.rqb200_dbg_rows_gemm(N.ptr(X), N.ptr(W), N.ptr(bias), N.ptr(out), N.ptr(out), None, 0, code, M, N_out, K, N.stream_ptr()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out[:M], ref + R, rtol=1e-4, atol=1e-4)
+    assert bool((out[M:] == 7.0).all())
+    o16 = torch.full((M + 3, N_out), 7.0, dtype=dt, device=DEV)
+    N.check(L.rqb200_dbg_rows_gemm(N.ptr(X), N.ptr(W), N.ptr(bias), None, None, N.ptr(o16), 1, code, M, N_out, K, N.stream_ptr()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(o16[:M].float(), gelu(ref).to(dt).float(), rtol=2e-2, atol=2e-2)
+    assert bool((o16[M:] == 7.0).all())

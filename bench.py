@@ -38,7 +38,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), or None
-TRAFFIC_NCU = {"gemm_tc_fc2": 19702016}   # profiles/ncu_gemm_tc_r1_raw.csv, fc2 launch: 19.70 MB read + 0 B written (partials stay in L2)
+TRAFFIC_NCU = {"gemm_tc_fc2": 19736320}   # profiles/ncu_ar_chain_r2_raw.csv, fc2 launch: 19.74 MB read + 0 B written (partials stay in L2)
 
 MODELS = {
     # name: (E, heads, n_body, n_head_layers, V, block, vocab_cond, cond_len, vae attn_res, vae ch_mult, top_p, default B, text)

@@ -45,11 +45,8 @@ extern "C" {
 #define RQB200_AR_L2_PREFETCH 8         /* GEMMs prefetch into L2 the weight boxes that do not fit their shared-memory ring */
 #define RQB200_AR_SHALLOW_RING 16       /* half-depth GEMM rings: two GEMM CTAs of consecutive launches share an SM        */
 #define RQB200_AR_SEQUENTIAL_PREFILL 32 /* prefill the prefix token by token with the single-step graph (the prefill oracle) */
-#define RQB200_AR_NO_NEXT_PREFETCH 64   /* fc1 does not pull fc2's weights into L2                                          */
-#define RQB200_AR_NO_KV_PREFETCH 256    /* attention does not pull the next layer's cache rows into L2 ahead of time          */
-#define RQB200_AR_BATCHED_DEEP_RING 512 /* large-M passes (prefill / forward) keep the deep ring: one CTA per SM                  */
-#define RQB200_AR_BATCHED_STREAMER 1024 /* large-M passes through the weight-streaming GEMM instead of the persistent rows GEMM    */
-#define RQB200_AR_LN_CLUSTER 128        /* reduction + LayerNorm rows split over 2-CTA clusters (DSMEM statistics exchange)  */
+#define RQB200_AR_BATCHED_DEEP_RING 64  /* large-M passes (prefill / forward) keep the deep ring: one CTA per SM                  */
+#define RQB200_AR_BATCHED_STREAMER 128  /* large-M passes through the weight-streaming GEMM instead of the persistent rows GEMM    */
 
 const char* rqb200_last_error(void);
 int rqb200_version(void);

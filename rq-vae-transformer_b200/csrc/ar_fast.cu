@@ -128,90 +128,6 @@ ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ parti
     TR_OUT(tr);
 }
 
-// The same reduction + LayerNorm with each row split over a 2-CTA thread-block cluster (128 CTAs at B = 64 instead of 64: the
-// kernel is bound by one SM pulling S x E x 4 B of partials out of L2).  Each CTA owns half of the features; the halves exchange
-// (mean, M2) once through distributed shared memory and combine them exactly (Chan).  E % 8 == 0, E / 8 <= 3 * 192.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
-ln_reduce2_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int S, const float* __restrict__ bias,
-                  const float* __restrict__ extra, float* __restrict__ x_out, const float* __restrict__ g,
-                  const float* __restrict__ be, h16* __restrict__ xn, int B, int E, int bf, long long* tr) {
-    __shared__ float red[33];
-    __shared__ float xchg[2];
-    tc::pdl_launch_dependents();
-    TR_IN(tr);
-    tc::pdl_wait();
-    TR_DEP(tr);
-    const int b = blockIdx.x >> 1, rank = blockIdx.x & 1;
-    const int E4h = E >> 3, base4 = rank * E4h;          // float4 chunks per half
-    const int S12 = S < 12 ? S : 12;
-    float4 v[3], gg[3], bb[3];
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int i4 = threadIdx.x + k * 192, e4 = base4 + i4;
-        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i4 < E4h) {
-            float4 pr[12];
-            if (xn) { gg[k] = reinterpret_cast<const float4*>(g)[e4]; bb[k] = reinterpret_cast<const float4*>(be)[e4]; }
-#pragma unroll
-            for (int i = 0; i < 12; i++)
-                if (i < S12) pr[i] = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
-            if (x_in) v[k] = reinterpret_cast<const float4*>(x_in + (int64_t)b * E)[e4];
-            if (bias) { float4 t = reinterpret_cast<const float4*>(bias)[e4]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
-#pragma unroll
-            for (int i = 0; i < 12; i++)
-                if (i < S12) { v[k].x += pr[i].x; v[k].y += pr[i].y; v[k].z += pr[i].z; v[k].w += pr[i].w; }
-            for (int i = 12; i < S; i++) {
-                float4 p0 = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
-                v[k].x += p0.x; v[k].y += p0.y; v[k].z += p0.z; v[k].w += p0.w;
-            }
-            if (extra) { float4 t = reinterpret_cast<const float4*>(extra)[e4]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
-            if (x_out) reinterpret_cast<float4*>(x_out + (int64_t)b * E)[e4] = v[k];
-            s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-        }
-    }
-    if (xn) {                                             // (uniform over the cluster: both halves take the same branch)
-        const float nh = (float)(E >> 1);
-        const float lmean = block_sum(s, red) / nh;
-        float q = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            if (threadIdx.x + k * 192 < E4h) {
-                const float d0 = v[k].x - lmean, d1 = v[k].y - lmean, d2 = v[k].z - lmean, d3 = v[k].w - lmean;
-                q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
-            }
-        const float lm2 = block_sum(q, red);
-        if (threadIdx.x == 0) { xchg[0] = lmean; xchg[1] = lm2; }
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        uint32_t peer;
-        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(tc::smem_u32(xchg)), "r"((uint32_t)(rank ^ 1)));
-        float pmean, pm2;
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pmean) : "r"(peer) : "memory");
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pm2) : "r"(peer + 4) : "memory");
-        // combine in a rank-independent order so that both halves compute the same statistics bit for bit
-        const float m_lo = rank == 0 ? lmean : pmean, m_hi = rank == 0 ? pmean : lmean;
-        const float q_lo = rank == 0 ? lm2 : pm2, q_hi = rank == 0 ? pm2 : lm2;
-        const float mean = 0.5f * (m_lo + m_hi);
-        const float dl = m_hi - m_lo;
-        const float rstd = rsqrtf(((q_lo + q_hi) + dl * dl * (0.5f * nh)) / (float)E + 1e-5f);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int i4 = threadIdx.x + k * 192, e4 = base4 + i4;
-            if (i4 < E4h) {
-                uint2 pk;
-                pk.x = pack_h16x2((v[k].x - mean) * rstd * gg[k].x + bb[k].x, (v[k].y - mean) * rstd * gg[k].y + bb[k].y, bf);
-                pk.y = pack_h16x2((v[k].z - mean) * rstd * gg[k].z + bb[k].z, (v[k].w - mean) * rstd * gg[k].w + bb[k].w, bf);
-                reinterpret_cast<uint2*>(xn + (int64_t)b * E)[e4] = pk;
-            }
-        }
-        // the peer may still be reading this CTA's exchange slot
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    }
-    TR_OUT(tr);
-}
-
 // h = 16-bit(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K); 4 elements per thread, all partial loads in flight
 __global__ void __launch_bounds__(256)
 act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, h16* __restrict__ h, int B, int N, int bf,
@@ -249,21 +165,14 @@ act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restr
 // one warp per (b, head): reduce the split-K qkv partials (+bias), append k,v at row t of the 16-bit cache, attend.
 // lane <-> dims (2*lane, 2*lane+1) for q/k/v/out everywhere: every cache row is read as ONE coalesced 128 B line per warp
 // instruction (a lane-per-key row read costs 8x the L1 wavefronts); the per-key dot products are finished with a 31-shuffle
-// transpose-reduce per 32 keys, after which lane j holds the score of key j.  T <= 512.
-// The cached rows [0, t) were written by EARLIER graph replays, so they do not depend on the upstream kernel of the chain.  At
-// T = 64, B = 64 one layer's rows are 25 MB -- 3.9 us of HBM time that used to sit behind two dependent round trips.  With
-// early_t the warp pulls rows into L2 BEFORE griddepcontrol.wait: the NEXT layer's rows (kc_pf / vc_pf: a whole block of lead
-// time) and, when pf_self is set (first layer of a stack), its own.  After the wait up to 64 K rows / 64 V rows are in flight.
+// transpose-reduce per 32 keys, after which lane j holds the score of key j.  Up to 64 K rows / 64 V rows are in flight at once
+// and the V rows are requested before the softmax arithmetic.  T <= 512.
+// (Measured and dropped in round 2: pulling the cached rows into L2 ahead of griddepcontrol.wait -- from this kernel or from the
+// previous layer's -- changes nothing (the two 64-row phases cost 4.4 us each at T = 64 either way); reading them into registers
+// ahead of the wait is a race in the head graph, where the producer of row d-1 is a kernel of the SAME graph that a chain of
+// small launches does not keep from still being in flight.)
 constexpr int AF_MAXT = 512;
 
-// rows [0, t) of one (b, head) are t * 128 contiguous bytes: one bulk L2 prefetch per 16 KB
-__device__ __forceinline__ void af_prefetch_rows(const h16* base, int t, int lane) {
-    const int chunks = (t + 127) >> 7;
-    if (lane < chunks) {
-        const int rows = (t - lane * 128) < 128 ? (t - lane * 128) : 128;
-        tc::bulk_prefetch_l2(base + (int64_t)lane * 128 * 64, (uint32_t)rows * 128u);
-    }
-}
 // pv[u] = this lane's partial dot product for key u (u < 32); returns the full dot product of key `lane`
 __device__ __forceinline__ float af_transpose_reduce(float (&pv)[32], int lane) {
 #pragma unroll
@@ -281,45 +190,22 @@ __device__ __forceinline__ float af_transpose_reduce(float (&pv)[32], int lane) 
 
 __global__ void __launch_bounds__(128)
 attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, h16* __restrict__ kc, h16* __restrict__ vc,
-                 h16* __restrict__ att, int B, int E, int nh, int Tmax, const int* __restrict__ t_ptr, int t_host, int early_t,
-                 const h16* __restrict__ kc_pf, const h16* __restrict__ vc_pf, int pf_self, int bf, long long* tr) {
+                 h16* __restrict__ att, int B, int E, int nh, int Tmax, const int* __restrict__ t_ptr, int t_host, int bf,
+                 long long* tr) {
     extern __shared__ float af_smem[];              // ps[4][tp]
     const int tp = (Tmax + 31) & ~31;
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     float* ps = af_smem + wq * tp;
     tc::pdl_launch_dependents();
     TR_IN(tr);
-    const int bh = blockIdx.x * 4 + wq;
-    const bool valid = bh < B * nh;
-    const int b = valid ? bh / nh : 0, h = valid ? bh % nh : 0;
-    const int64_t pair = ((int64_t)(b * nh + h) * Tmax) * 64;
-    h16* kb = kc + pair;
-    h16* vb = vc + pair;
-    int t = 0;
-    uint32_t kr[64];                               // K rows [0, min(t, 64)) of this (b, head): lane <-> 2 dims
-    if (early_t) {
-        // (position counters are only advanced by the LAST kernel of a graph; no kernel upstream of this one in the graph writes them)
-        t = t_ptr ? *reinterpret_cast<const volatile int*>(t_ptr) : t_host;
-        if (valid) {
-            if (pf_self) { af_prefetch_rows(vb, t, lane); if (t > 64) af_prefetch_rows(kb, t, lane); }
-            if (kc_pf) { af_prefetch_rows(kc_pf + pair, t, lane); af_prefetch_rows(vc_pf + pair, t, lane); }
-            // the first 64 cached K rows go straight into registers: their round trip overlaps the wait for the qkv GEMM
-#pragma unroll
-            for (int u = 0; u < 64; u++)
-                kr[u] = (u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)u * 64 + 2 * lane) : 0u;
-        }
-    }
     tc::pdl_wait();
     TR_DEP(tr);
-    if (!early_t) {
-        t = t_ptr ? *t_ptr : t_host;
-        if (valid) {
-#pragma unroll
-            for (int u = 0; u < 64; u++)
-                kr[u] = (u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)u * 64 + 2 * lane) : 0u;
-        }
-    }
-    if (valid) {
+    const int bh = blockIdx.x * 4 + wq;
+    if (bh < B * nh) {
+    const int b = bh / nh, h = bh % nh;
+    const int t = t_ptr ? *t_ptr : t_host;
+    h16* kb = kc + ((int64_t)(b * nh + h) * Tmax) * 64;
+    h16* vb = vc + ((int64_t)(b * nh + h) * Tmax) * 64;
     const int c = h * 64 + 2 * lane;
     float2 q = make_float2(bqkv[c], bqkv[c + 1]);
     float2 k = make_float2(bqkv[E + c], bqkv[E + c + 1]);
@@ -339,12 +225,11 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     const float2 qf = unpack_h16x2(pack_h16x2(q.x, q.y, bf), bf), kf = unpack_h16x2(k2, bf), vf = unpack_h16x2(v2, bf);
     const float s_new = warp_sum(qf.x * kf.x + qf.y * kf.y) * 0.125f;
     float m = s_new;
-    for (int j0 = 0; j0 < t; j0 += 64) {          // scores of the cached rows, 64 at a time
-        if (j0 > 0) {                              // (T > 64 only: the later rows are fetched here)
+    for (int j0 = 0; j0 < t; j0 += 64) {          // scores of the cached rows: 64 coalesced row reads in flight
+        uint32_t kr[64];
 #pragma unroll
-            for (int u = 0; u < 64; u++)
-                kr[u] = (j0 + u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)(j0 + u) * 64 + 2 * lane) : 0u;
-        }
+        for (int u = 0; u < 64; u++)
+            kr[u] = (j0 + u < t) ? *reinterpret_cast<const uint32_t*>(kb + (int64_t)(j0 + u) * 64 + 2 * lane) : 0u;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             if (j0 + half * 32 < t) {                                  // (warp-uniform)
@@ -551,7 +436,7 @@ struct ArFast {
     cudaGraphExec_t graphs[G_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     int64_t n_nodes[G_COUNT] = {0, 0, 0, 0};   // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
-    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, next_pf = true, ln_cluster = false, kv_pf = true, batched_deep = false, batched_streamer = false;
+    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, batched_deep = false, batched_streamer = false;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
     int n_sm = 148;
     // diagnostic stage trace (cfg.flags & RQB200_AR_TRACE)
@@ -634,10 +519,8 @@ static GemmTcParams gemm_base(const ArFast& f, int N_out, int K, int rows, int s
 
 static int gemm(const ArFast& f, const char* name, const CUtensorMap& tw, const CUtensorMap& tx, int N_out, int K, int B, int splits,
                 int mode, const float* bias, float bias_scale, void* out, float* partial, const float* residual, int64_t ld_res,
-                const int* res_row_ptr, int64_t res_row_stride, cudaStream_t st, const void* next_w = nullptr,
-                int64_t next_w_bytes = 0) {
+                const int* res_row_ptr, int64_t res_row_stride, cudaStream_t st) {
     GemmTcParams p = gemm_base(f, N_out, K, B, splits, mode);
-    p.next_w = f.next_pf ? next_w : nullptr; p.next_w_bytes = next_w_bytes;
     p.bias = bias; p.bias_scale = bias_scale; p.out = out; p.partial = partial;
     p.residual = residual; p.ld_res = ld_res; p.res_row_ptr = res_row_ptr; p.res_row_stride = res_row_stride;
     p.trace = tr_slot(f, name);
@@ -646,38 +529,16 @@ static int gemm(const ArFast& f, const char* name, const CUtensorMap& tw, const 
 
 static int ln(const ArFast& f, const char* name, int rows, const float* x_in, const float* partial, int S, const float* bias,
               const float* extra, float* x_out, const float* g, const float* be, h16* xn, cudaStream_t st) {
-    if (f.ln_cluster && f.cfg.embed_dim % 8 == 0 && f.cfg.embed_dim / 8 <= 3 * 192) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)rows * 2);
-        cfg.blockDim = dim3(192);
-        cfg.stream = st;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = f.use_pdl ? 1 : 0;
-        at[1].id = cudaLaunchAttributeClusterDimension;
-        at[1].val.clusterDim.x = 2;
-        at[1].val.clusterDim.y = 1;
-        at[1].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 2;
-        RQB_CUDA(cudaLaunchKernelEx(&cfg, ln_reduce2_kernel, x_in, partial, S, bias, extra, x_out, g, be, xn, rows, f.cfg.embed_dim, f.bf,
-                                    tr_slot(f, name)));
-        g_launches++;
-        return 0;
-    }
     return launch_pdl(ln_reduce_kernel, dim3((unsigned)rows), dim3(384), (size_t)0, st, f.use_pdl, x_in, partial, S, bias, extra, x_out, g,
                       be, xn, rows, f.cfg.embed_dim, f.bf, tr_slot(f, name));
 }
 
 static int attn(const ArFast& f, FastWs& ws, const float* bqkv, h16* kc, h16* vc, int Tmax, const int* t_ptr, int t_host,
-                const h16* kc_next, const h16* vc_next, bool first, cudaStream_t st) {
+                cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
     const size_t smem = (size_t)(4 * ((Tmax + 31) & ~31)) * sizeof(float);
-    // reading the position counter ahead of the dependency is only safe inside a captured graph (see the kernel)
-    const int early = (f.use_graph || t_ptr == nullptr) ? 1 : 0;
     return launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(f.B * c.n_head, 4)), dim3(128), smem, st, f.use_pdl,
-                      (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, t_ptr, t_host, early,
-                      f.kv_pf ? kc_next : (const h16*)nullptr, f.kv_pf ? vc_next : (const h16*)nullptr, (first || !f.kv_pf) ? 1 : 0, f.bf,
+                      (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, t_ptr, t_host, f.bf,
                       tr_slot(f, "attn"));
 }
 
@@ -701,20 +562,15 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
                    first ? pending_extra : nof, x, bw.ln1_w, bw.ln1_b, ws.XN, st));
         RQB_TRY(gemm(f, "qkv", maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr, 0,
                      st));
-        const bool has_next = l + 1 < blocks.size();
-        RQB_TRY(attn(f, ws, bw.bqkv, kc + per * l, vc + per * l, Tmax, t_ptr, t_host, has_next ? kc + per * (l + 1) : nullptr,
-                     has_next ? vc + per * (l + 1) : nullptr, first, st));
+        RQB_TRY(attn(f, ws, bw.bqkv, kc + per * l, vc + per * l, Tmax, t_ptr, t_host, st));
         RQB_TRY(gemm(f, "proj", maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr,
                      0, st));
         RQB_TRY(ln(f, "ln2", B, x, ws.P, f.split_proj, bw.bproj, nof, x, bw.ln2_w, bw.ln2_b, ws.XN, st));
         if (f.split_fc1 == 1) {
-            RQB_TRY(gemm(f, "fc1", maps[l].fc1, f.tx_xn, 4 * E, E, B, 1, GT_H16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr, 0, st,
-                         bw.w2, (int64_t)E * 4 * E * 2));
+            RQB_TRY(gemm(f, "fc1", maps[l].fc1, f.tx_xn, 4 * E, E, B, 1, GT_H16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr, 0, st));
         } else {
-            // fc2 only becomes resident when fc1's CTAs leave (shared memory) and act_reduce is short: its weights would stream
-            // from HBM on the critical path -- fc1's idle producer thread pulls them into L2 meanwhile
             RQB_TRY(gemm(f, "fc1", maps[l].fc1, f.tx_xn, 4 * E, E, B, f.split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
-                         nullptr, 0, st, bw.w2, (int64_t)E * 4 * E * 2));
+                         nullptr, 0, st));
             RQB_TRY(launch_pdl(act_reduce_kernel, dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)B * 4 * E / 4, 256), 1184)), dim3(256),
                                (size_t)0, st, f.use_pdl, (const float*)ws.P, f.split_fc1, bw.b1, ws.Hh, B, 4 * E, f.bf,
                                tr_slot(f, "act_reduce")));
@@ -825,9 +681,6 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     f->l2pf = (cfg.flags & RQB200_AR_L2_PREFETCH) != 0;
     f->deep = !(cfg.flags & RQB200_AR_SHALLOW_RING);
     f->batched_prefill = !(cfg.flags & RQB200_AR_SEQUENTIAL_PREFILL);
-    f->next_pf = !(cfg.flags & RQB200_AR_NO_NEXT_PREFETCH);
-    f->ln_cluster = (cfg.flags & RQB200_AR_LN_CLUSTER) != 0;
-    f->kv_pf = !(cfg.flags & RQB200_AR_NO_KV_PREFETCH);
     f->batched_deep = (cfg.flags & RQB200_AR_BATCHED_DEEP_RING) != 0;
     f->batched_streamer = (cfg.flags & RQB200_AR_BATCHED_STREAMER) != 0;
     {

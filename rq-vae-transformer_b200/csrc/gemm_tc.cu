@@ -196,15 +196,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if (tr) p.trace[1] = tc::gtimer();
             for (int i = 0; i < pre; i++)
                 tc::tma_load_2d(smem + i * STAGE_BYTES + GT_A_BYTES, &tmX, &full[i], (kb0 + i) * 64, m0, tc::L2_EVICT_LAST);
-            if (p.next_w != nullptr) {
-                const int64_t ctas = (int64_t)gridDim.x * gridDim.y, me = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
-                const int64_t per = ((p.next_w_bytes + ctas - 1) / ctas + 127) & ~(int64_t)127;
-                const int64_t b0 = me * per, b1 = (b0 + per) < p.next_w_bytes ? (b0 + per) : p.next_w_bytes;
-                for (int64_t o = b0; o < b1; o += 16384) {
-                    const int64_t nbytes = (b1 - o) < 16384 ? (b1 - o) : 16384;
-                    tc::bulk_prefetch_l2(reinterpret_cast<const char*>(p.next_w) + o, (uint32_t)(nbytes & ~(int64_t)15));
-                }
-            }
             for (int i = pre; i < nkb; i++) {
                 const int s = i % STAGES;
                 tc::mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);

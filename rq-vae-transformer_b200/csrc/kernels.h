@@ -72,10 +72,6 @@ struct GemmTcParams {
     int fmt;                      // 16-bit operand / output format: 0 = fp16 (the reference's autocast class), 1 = bf16
     int deep;                     // 1: deepest shared-memory ring (one CTA per SM); 0: half depth (two CTAs of consecutive launches per SM)
     int l2pf;                     // 1: before waiting for the upstream kernel, prefetch into L2 the weight boxes that do not fit the ring
-    // once this launch's own loads are issued, every CTA prefetches its 1/grid share of [next_w, next_w + next_w_bytes) into L2: the
-    // weights of a LATER launch whose own prefetch window is too short (fc2 behind fc1 + act_reduce).  nullable.
-    const void* next_w;
-    int64_t next_w_bytes;
     const float* bias;            // [N_out] (nullable); added as bias * bias_scale
     float bias_scale;
     // GT_F32 only: out = acc + bias + residual[(row0 * res_row_stride) + b * ld_res + n], row0 = res_row_ptr ? *res_row_ptr : 0

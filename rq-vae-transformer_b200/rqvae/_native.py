@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("RQB200_LIB", os.path.join(os.path.dirname(_HERE), "cs
 OK, EINVAL, ECUDA, ENODEV, EWORKSPACE, ESTATE = 0, -1, -2, -3, -4, -5
 F32, BF16, F16 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
-AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_NO_NEXT_PREFETCH, AR_LN_CLUSTER, AR_NO_KV_PREFETCH, AR_BATCHED_DEEP_RING, AR_BATCHED_STREAMER = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
+AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_BATCHED_DEEP_RING, AR_BATCHED_STREAMER = 1, 2, 4, 8, 16, 32, 64, 128
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 c_f32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p
@@ -169,9 +169,6 @@ def ar_engine_options():
     flags |= AR_L2_PREFETCH if env("RQB200_GEMM_L2PF", "0") == "1" else 0
     flags |= AR_SHALLOW_RING if env("RQB200_GEMM_SHALLOW", "0") == "1" else 0
     flags |= AR_SEQUENTIAL_PREFILL if env("RQB200_SEQ_PREFILL", "0") == "1" else 0
-    flags |= AR_NO_NEXT_PREFETCH if env("RQB200_NO_NEXT_PF", "0") == "1" else 0
-    flags |= AR_LN_CLUSTER if env("RQB200_LN_CLUSTER", "0") == "1" else 0
-    flags |= AR_NO_KV_PREFETCH if env("RQB200_NO_KV_PF", "0") == "1" else 0
     flags |= AR_BATCHED_DEEP_RING if env("RQB200_BATCHED_DEEP", "0") == "1" else 0
     flags |= AR_BATCHED_STREAMER if env("RQB200_BATCHED_STREAMER", "0") == "1" else 0
     return {"flags": flags,

@@ -131,11 +131,6 @@ def test_fast_tier_free_running_consistency(golden, layouts):
     for var in ("RQB200_NO_GRAPH", "RQB200_NO_PDL", "RQB200_GEMM_SHALLOW", "RQB200_GEMM_L2PF", "RQB200_TRACE"):
         d = _with_env(model, {var: "1"}, lambda: model._native_sample(part, aux, cond, (0, 0), 1.0, 100, 0.95, True, noise=noise))
         assert torch.equal(a, d), var
-    # 2-CTA-cluster LayerNorm rows: the same statistics up to the order of one fp32 combination
-    _, lg_a = model._native_sample(a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a)
-    _, lg_c = _with_env(model, {"RQB200_LN_CLUSTER": "1"}, lambda: model._native_sample(
-        a, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=a))
-    assert float((lg_a - lg_c).abs().max()) < 2e-3 * float(lg_a.std())
     # noise drawn span by span (bounded buffer, KV state resumed between spans) == one call with the whole noise tensor
     torch.manual_seed(4321)
     full = torch.empty(n_tok, B, V, device=DEV)

@@ -154,12 +154,15 @@ int64_t rqb200_ar_last_launches(const rqb200_ar* h);
 
 /* ------------------------------------------------------------------------------------------------ P2
  * RQVAE encode / decode (rqvae/models/rqvae/rqvae.py:80-109; modules.py:73-98,171-202; layers.py). */
+/* OR-ed into rqb200_vae_config.mode (fast tier; diagnostics): GroupNorm statistics by the stand-alone gn_stats pass instead of the
+ * producing conv's epilogue */
+#define RQB200_VAE_NO_GN_FUSE 0x100
 typedef struct rqb200_vae_config {
     int32_t ch, n_levels, ch_mult[8], num_res_blocks;
     int32_t n_attn_res, attn_resolutions[8];
     int32_t resolution, z_channels, embed_dim, in_channels, out_ch;
     int32_t codebook_size, depth;     /* K, D */
-    int32_t mode;                     /* RQB200_MODE_*: EXACT = f32 conv weights, FAST = f16 conv weights */
+    int32_t mode;                     /* RQB200_MODE_*: EXACT = f32 conv weights, FAST = f16 conv weights; | RQB200_VAE_* flags */
 } rqb200_vae_config;
 
 typedef struct rqb200_vae rqb200_vae;

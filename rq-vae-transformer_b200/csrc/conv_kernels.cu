@@ -129,7 +129,9 @@ int launch_conv(const float* X, const void* W, int wdtype, const float* bias, co
 constexpr int GN_PIX = 256;       // pixels per CTA
 constexpr int GN_G = 32;
 
-size_t groupnorm_ws_doubles(int B, int HW) { return (size_t)B * ceil_div(HW, GN_PIX) * GN_G * 2 + (size_t)B * GN_G * 2; }
+// partial statistics: one (sum, sum of squares) pair per group and per chunk of 32 pixels (the conv epilogue's granularity; the
+// stand-alone gn_stats_kernel uses every 8th slot's worth), then the finalised (mean, rstd) pairs
+size_t groupnorm_ws_doubles(int B, int HW) { return (size_t)B * ceil_div(HW, 32) * GN_G * 2 + (size_t)B * GN_G * 2; }
 
 // lane == group: a warp reads one pixel's C contiguous channels, lane l owns channels [l*cg, (l+1)*cg)
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ X, double* __restrict__ part, int HW, int C) {

@@ -35,6 +35,11 @@ struct ConvTcParams {
     void* out16;                   // non-null: 16-bit NHWC output (fmt) instead of `out`, optionally through GELU
     int gelu, fmt;                 // fmt: 16-bit operand / output format, 0 fp16 (all convs), 1 bf16
     int64_t m_rows;                // > 0: only pixels (rows) below m_rows are stored
+    // GroupNorm(32) statistics of the OUTPUT (bias / residual included), for the GroupNorm that consumes it next (layers.py:16-17,
+    // 100-120): every epilogue warp (32 pixels of one image) writes (sum, sum of squares) per group as fp64 to
+    // gn_part[((b * gn_chunks + chunk) * 32 + group) * 2] -- the partial layout gn_finalize_kernel reduces.  NULL: off.
+    double* gn_part;
+    int gn_chunks;                 // H * W / 32
 };
 
 constexpr int CT_THREADS = 192;
@@ -157,8 +162,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
                 const int n0 = nt * BN + c0;
-                if (!valid || n0 >= p.Cout) continue;
+                if (n0 >= p.Cout) continue;                                 // (warp-uniform)
                 if (p.out_nchw) {
+                    if (!valid) continue;
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         const int n = n0 + i;
@@ -166,6 +172,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             p.out[(((int64_t)b * p.Cout + n) * p.H + y) * p.W + x] = __uint_as_float(v[i]) + p.bias[n];
                     }
                 } else if (p.out16 != nullptr) {
+                    if (!valid) continue;
                     float w[16];
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
@@ -187,16 +194,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     float* o = p.out + pix * p.Cout + n0;
                     const float* rs = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+                    float wv[16];
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
                         float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + i);
                         float4 w = make_float4(__uint_as_float(v[i]) + bb.x, __uint_as_float(v[i + 1]) + bb.y,
                                                __uint_as_float(v[i + 2]) + bb.z, __uint_as_float(v[i + 3]) + bb.w);
-                        if (rs) {
+                        if (rs && valid) {
                             float4 rr = *reinterpret_cast<const float4*>(rs + i);
                             w.x += rr.x; w.y += rr.y; w.z += rr.z; w.w += rr.w;
                         }
-                        *reinterpret_cast<float4*>(o + i) = w;
+                        if (valid) *reinterpret_cast<float4*>(o + i) = w;
+                        wv[i] = w.x; wv[i + 1] = w.y; wv[i + 2] = w.z; wv[i + 3] = w.w;
+                    }
+                    if (p.gn_part != nullptr) {
+                        // this warp's 32 pixels belong to one image (TW*TH >= 32, checked by the host); cg = 4 | 8 | 16 channels
+                        const int cg = p.Cout >> 5, ngr = 16 / cg;
+                        const int wpi = (p.TW * p.TH) >> 5;                      // warps (32-pixel chunks) per image within a tile
+                        const int chunk = (ty * p.tiles_x + tx) * wpi + (q % wpi);
+                        const int bw = tb * p.NB + (q * 32) / (p.TW * p.TH);      // image of this warp
+#pragma unroll
+                        for (int gi = 0; gi < 4; gi++) {
+                            if (gi < ngr) {                                       // (warp-uniform)
+                                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 16; i++)
+                                    if (i / cg == gi && valid) { s1 += wv[i]; s2 = fmaf(wv[i], wv[i], s2); }
+                                s1 = warp_sum(s1);
+                                s2 = warp_sum(s2);
+                                if (lane == 0 && bw < p.B) {
+                                    double* dst = p.gn_part + (((int64_t)bw * p.gn_chunks + chunk) * 32 + (n0 / cg + gi)) * 2;
+                                    dst[0] = (double)s1;
+                                    dst[1] = (double)s2;
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -241,11 +273,19 @@ bool conv_tc_supported(int H, int W, int Cin, int Cout, int ks, int stride, int 
     return pow2(H) && pow2(W);
 }
 
+// the epilogue can emit the output's GroupNorm(32) partial statistics when every epilogue warp's 32 pixels lie in one image and
+// a 16-channel chunk holds whole groups
+bool conv_tc_gn_fusable(int H, int W, int Cout) {
+    const int TW = W < 16 ? W : 16, TH = (128 / TW) < H ? (128 / TW) : H;
+    const int cg = Cout / 32;
+    return Cout % 32 == 0 && (cg == 4 || cg == 8 || cg == 16) && TW * TH >= 32 && (H * W) % 32 == 0;
+}
+
 // X: NHWC fp16 [B,H*stride,W*stride,Cin]; Wt: [Cout, ks, ks, Cin] fp16; out fp32 [B,H,W,Cout].  X16lo/W16lo non-null -> split-fp16
 // (3 products).  H, W are the OUTPUT extent.
 int launch_conv_tc(const void* X16, const void* W16, const void* X16lo, const void* W16lo, const float* bias,
                    const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ks, int out_nchw,
-                   cudaStream_t st, int stride) {
+                   cudaStream_t st, int stride, double* gn_part) {
     ConvTcParams p = {};
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ks; p.stride = stride;
     p.TW = W < 16 ? W : 16;
@@ -256,6 +296,11 @@ int launch_conv_tc(const void* X16, const void* W16, const void* X16lo, const vo
     const int BN = Cout <= 16 ? 16 : (Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64));
     p.n_tiles_n = (int)ceil_div(Cout, BN);
     p.bias = bias; p.residual = residual; p.out = out; p.out_nchw = out_nchw;
+    if (gn_part != nullptr) {
+        if (!conv_tc_gn_fusable(H, W, Cout) || out_nchw) return fail(RQB200_EINVAL, "conv_tc: GroupNorm statistics cannot be fused for this shape");
+        p.gn_part = gn_part;
+        p.gn_chunks = H * W / 32;
+    }
     CUtensorMap tmA, tmB;
     RQB_TRY(make_tmap_4d_nhwc(&tmA, X16, (uint64_t)Cin, (uint64_t)W * stride, (uint64_t)H * stride, (uint64_t)B, 64, (uint32_t)p.TW,
                               (uint32_t)p.TH, (uint32_t)p.NB, (uint32_t)stride));
@@ -324,17 +369,20 @@ __device__ __forceinline__ void store_split4(__half* hi, __half* lo, const float
     }
 }
 
-// one thread per (image, group): reduce the per-chunk fp64 partial sums once (instead of once per apply CTA)
+// one warp per (image, group): reduce the per-chunk fp64 partial sums once (instead of once per apply CTA); fixed order
 __global__ void gn_finalize_kernel(double* __restrict__ part, int B, int nchunks, double n, double eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= B * 32) return;
     const int b = i / 32, g = i % 32;
     double ts = 0.0, tss = 0.0;
-    for (int c = 0; c < nchunks; c++) {
+    for (int c = lane; c < nchunks; c += 32) {
         const double* o = part + (((int64_t)b * nchunks + c) * 32 + g) * 2;
         ts += o[0];
         tss += o[1];
     }
+    ts = warp_sum_d(ts);
+    tss = warp_sum_d(tss);
+    if (lane != 0) return;
     double mean = ts / n, var = tss / n - mean * mean;
     if (var < 0.0) var = 0.0;
     double* fin = part + (int64_t)B * nchunks * 64 + (int64_t)i * 2;
@@ -407,12 +455,14 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
     }
 }
 
+// fused_chunks > 0: the partial statistics were already written by the producing conv's epilogue (fused_chunks = HW / 32 partials
+// per image and group); otherwise gn_stats_kernel computes them (HW / 256 partials)
 int launch_groupnorm_f16(const float* X, const float* gamma, const float* beta, void* Y16, void* Y16lo, double* stats_ws, int B,
-                         int HW, int C, int silu, cudaStream_t st) {
+                         int HW, int C, int silu, cudaStream_t st, int fused_chunks) {
     if (C % 128 != 0) return fail(RQB200_EINVAL, "groupnorm_f16: C % 128 != 0");
-    const int nchunks = (int)ceil_div(HW, 256);
-    RQB_TRY(launch_gn_stats(X, stats_ws, B, HW, C, st));
-    gn_finalize_kernel<<<(unsigned)ceil_div(B * 32, 128), 128, 0, st>>>(stats_ws, B, nchunks, (double)HW * (C / 32), 1e-6);
+    const int nchunks = fused_chunks > 0 ? fused_chunks : (int)ceil_div(HW, 256);
+    if (fused_chunks <= 0) RQB_TRY(launch_gn_stats(X, stats_ws, B, HW, C, st));
+    gn_finalize_kernel<<<(unsigned)ceil_div(B * 32 * 32, 128), 128, 0, st>>>(stats_ws, B, nchunks, (double)HW * (C / 32), 1e-6);
     RQB_TRY(check_launch("gn_finalize"));
     int gx = (int)std::min<int64_t>(ceil_div((int64_t)HW * C / 8, 256), 1024);
     gn_apply_f16_kernel<<<dim3(gx, B), 256, 0, st>>>(X, stats_ws, gamma, beta, (__half*)Y16, (__half*)Y16lo, HW, C, 1e-6f, silu, nchunks);
@@ -437,7 +487,7 @@ extern "C" int rqb200_dbg_conv_tc(const void* X16, const void* W16, const void* 
     const int stride = (out_nchw >> 8) > 1 ? (out_nchw >> 8) : 1;
     if (!rqb::conv_tc_supported(H, W, Cin, Cout, ks, stride, 0)) return rqb::fail(RQB200_EINVAL, "conv_tc: unsupported shape");
     return rqb::launch_conv_tc(X16, W16, X16lo, W16lo, bias, residual, out, B, H, W, Cin, Cout, ks, out_nchw & 1, (cudaStream_t)stream,
-                               stride);
+                               stride, nullptr);
 }
 
 // diagnostic entry point: the rows GEMM (tests/test_gpu_tc.py).  X must have ceil(M/128)*128 readable rows.

@@ -56,11 +56,12 @@ int launch_gn_stats(const float* X, double* stats_ws, int B, int HW, int C, cuda
 bool conv_tc_supported(int H, int W, int Cin, int Cout, int ks, int stride, int in_nchw);
 int launch_conv_tc(const void* X16, const void* W16, const void* X16lo, const void* W16lo, const float* bias,
                    const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ks, int out_nchw,
-                   cudaStream_t st, int stride = 1);
+                   cudaStream_t st, int stride = 1, double* gn_part = nullptr);
+bool conv_tc_gn_fusable(int H, int W, int Cout);
 int launch_rows_gemm_tc(const void* X16, const void* W16, const float* bias, const float* residual, float* out_f32, void* out_16,
                         int gelu, int fmt, int64_t M, int N_out, int K, cudaStream_t st);
 int launch_groupnorm_f16(const float* X, const float* gamma, const float* beta, void* Y16, void* Y16lo, double* stats_ws, int B,
-                         int HW, int C, int silu, cudaStream_t st);
+                         int HW, int C, int silu, cudaStream_t st, int fused_chunks = 0);
 int launch_cast_f16(const float* X, void* Y16, void* Y16lo, int B, int H, int W, int C, int upsample, cudaStream_t st);
 int make_tmap_4d_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_c,
                       uint32_t box_w, uint32_t box_h, uint32_t box_b, uint32_t stride = 1);

@@ -24,7 +24,8 @@ struct rqb200_vae {
     bool finalized = false;
     bool fast_ok = false;     // FAST mode and every decoder channel count is a multiple of 128
     bool split = false;       // split-fp16 (3 products per conv): "<key>.weight_lo" tensors registered
-    bool enc_fast = false;    // the encoder's stride-1 convs were registered in fp16 as well (RQB200_ENC_FAST=1): encode on the tcgen05 path
+    bool enc_fast = false;    // the encoder's convs were registered in fp16 as well: encode on the tcgen05 path
+    bool gn_fuse = true;      // conv epilogues emit the next GroupNorm's partial statistics (mode bit RQB200_VAE_NO_GN_FUSE clears it)
     int64_t last_launches = 0;
     int64_t max_act = 0;      // max H*W*C per image over all activations
     int64_t max_gn_hw = 0;
@@ -45,8 +46,11 @@ struct VaeRun {
     bool fast = false;
 
     // ---- fast tier helpers (tcgen05 implicit GEMM; decoder only, C % 128 == 0 everywhere)
+    // want_stats: the output feeds a GroupNorm next -> its epilogue emits the GroupNorm partial statistics (no gn_stats pass)
+    const float* stats_buf = nullptr;         // conv output whose statistics sit in gn_ws
+    int stats_chunks = 0;
     int conv_f(const std::string& name, const __half* in16, float* out, const float* resid, int Hh, int Ww, int Cin, int Cout,
-               int ks, int out_nchw, int stride = 1) {
+               int ks, int out_nchw, int stride = 1, bool want_stats = false) {
         const VTensor* w = get(name + ".weight", (int64_t)Cout * ks * ks * Cin);
         const VTensor* b = get(name + ".bias", Cout);
         note_act((int64_t)Hh * Ww, Cout);
@@ -60,20 +64,27 @@ struct VaeRun {
             w_lo = wl->ptr;
             in_lo = in16 == h16[0] ? l16[0] : l16[1];
         }
-        return launch_conv_tc(in16, w->ptr, in_lo, w_lo, (const float*)b->ptr, resid, out, B, Hh, Ww, Cin, Cout, ks, out_nchw, st, stride);
+        const bool fuse = want_stats && h->gn_fuse && !out_nchw && conv_tc_gn_fusable(Hh, Ww, Cout);
+        stats_buf = fuse ? out : nullptr;
+        stats_chunks = fuse ? Hh * Ww / 32 : 0;
+        return launch_conv_tc(in16, w->ptr, in_lo, w_lo, (const float*)b->ptr, resid, out, B, Hh, Ww, Cin, Cout, ks, out_nchw, st, stride,
+                              fuse ? gn_ws : nullptr);
     }
     int gn_f(const std::string& name, const float* in, __half* out16, int HW, int C, int silu) {
         const VTensor* g = get(name + ".weight", C);
         const VTensor* b = get(name + ".bias", C);
         if (HW > h->max_gn_hw) h->max_gn_hw = HW;
         if (dry || !g || !b) return 0;
-        return launch_groupnorm_f16(in, (const float*)g->ptr, (const float*)b->ptr, out16, out16 == h16[0] ? l16[0] : l16[1], gn_ws, B, HW, C, silu, st);
+        const int fused = (in == stats_buf) ? stats_chunks : 0;
+        stats_buf = nullptr;
+        return launch_groupnorm_f16(in, (const float*)g->ptr, (const float*)b->ptr, out16, out16 == h16[0] ? l16[0] : l16[1], gn_ws, B, HW, C, silu, st,
+                                    fused);
     }
     int resblock_f(const std::string& p, int cur, int Hh, int Ww, int Cin, int Cout, int* rc) {
         int a = (cur + 1) & 3, b = (cur + 2) & 3, c = (cur + 3) & 3;
         (void)a;
         *rc = gn_f(p + ".norm1", buf[cur], h16[0], Hh * Ww, Cin, 1); if (*rc) return cur;
-        *rc = conv_f(p + ".conv1", h16[0], buf[b], nullptr, Hh, Ww, Cin, Cout, 3, 0); if (*rc) return cur;
+        *rc = conv_f(p + ".conv1", h16[0], buf[b], nullptr, Hh, Ww, Cin, Cout, 3, 0, 1, true); if (*rc) return cur;
         *rc = gn_f(p + ".norm2", buf[b], h16[0], Hh * Ww, Cout, 1); if (*rc) return cur;
         const float* res = buf[cur];
         if (Cin != Cout) {
@@ -81,7 +92,7 @@ struct VaeRun {
             *rc = conv_f(p + ".nin_shortcut", h16[1], buf[c], nullptr, Hh, Ww, Cin, Cout, 1, 0); if (*rc) return cur;
             res = buf[c];
         }
-        *rc = conv_f(p + ".conv2", h16[0], buf[b], res, Hh, Ww, Cout, Cout, 3, 0);
+        *rc = conv_f(p + ".conv2", h16[0], buf[b], res, Hh, Ww, Cout, Cout, 3, 0, 1, true);
         return b;
     }
     int attnblock_f(const std::string& p, int cur, int Hh, int Ww, int C, int* rc) {
@@ -92,7 +103,7 @@ struct VaeRun {
             *rc = launch_vae_attn(buf[b], buf[a], B, Hh * Ww, C, st); if (*rc) return cur;
             *rc = launch_cast_f16(buf[a], h16[0], l16[0], B, Hh, Ww, C, 0, st); if (*rc) return cur;
         }
-        *rc = conv_f(p + ".proj_out", h16[0], buf[c], buf[cur], Hh, Ww, C, C, 1, 0);
+        *rc = conv_f(p + ".proj_out", h16[0], buf[c], buf[cur], Hh, Ww, C, C, 1, 0, 1, true);
         return c;
     }
     int decode_fast(const float* z, float* out) {
@@ -104,7 +115,7 @@ struct VaeRun {
         if (!dry) { rc = launch_cast_f16(z, h16[0], l16[0], B, res, res, c.embed_dim, 0, st); if (rc) return rc; }
         rc = conv_f("post_quant_conv", h16[0], buf[1], nullptr, res, res, c.embed_dim, c.z_channels, 1, 0); if (rc) return rc;
         if (!dry) { rc = launch_cast_f16(buf[1], h16[0], l16[0], B, res, res, c.z_channels, 0, st); if (rc) return rc; }
-        rc = conv_f("decoder.conv_in", h16[0], buf[0], nullptr, res, res, c.z_channels, ch, 3, 0); if (rc) return rc;
+        rc = conv_f("decoder.conv_in", h16[0], buf[0], nullptr, res, res, c.z_channels, ch, 3, 0, 1, true); if (rc) return rc;
         cur = resblock_f("decoder.mid.block_1", cur, res, res, ch, ch, &rc); if (rc) return rc;
         cur = attnblock_f("decoder.mid.attn_1", cur, res, res, ch, &rc); if (rc) return rc;
         cur = resblock_f("decoder.mid.block_2", cur, res, res, ch, ch, &rc); if (rc) return rc;
@@ -119,7 +130,7 @@ struct VaeRun {
             if (lvl != 0) {
                 int nxt = (cur + 1) & 3;
                 if (!dry) { rc = launch_cast_f16(buf[cur], h16[1], l16[1], B, res, res, ch, 1, st); if (rc) return rc; }   // x2 nearest, fp16
-                rc = conv_f("decoder.up." + std::to_string(lvl) + ".upsample.conv", h16[1], buf[nxt], nullptr, 2 * res, 2 * res, ch, ch, 3, 0);
+                rc = conv_f("decoder.up." + std::to_string(lvl) + ".upsample.conv", h16[1], buf[nxt], nullptr, 2 * res, 2 * res, ch, ch, 3, 0, 1, true);
                 if (rc) return rc;
                 cur = nxt;
                 res *= 2;
@@ -245,7 +256,7 @@ struct VaeRun {
                 // Downsample (layers.py:50-57): pad (0,1,0,1) + 3x3 stride 2 = the same implicit GEMM through a tensor map that
                 // samples every other pixel; the one-pixel right/bottom pad is its out-of-bounds fill
                 if (!dry) { rc = launch_cast_f16(buf[cur], h16[1], l16[1], B, res, res, ch, 0, st); if (rc) return rc; }
-                rc = conv_f(p + ".downsample.conv", h16[1], buf[nxt], nullptr, res / 2, res / 2, ch, ch, 3, 0, 2); if (rc) return rc;
+                rc = conv_f(p + ".downsample.conv", h16[1], buf[nxt], nullptr, res / 2, res / 2, ch, ch, 3, 0, 2, true); if (rc) return rc;
                 cur = nxt;
                 res /= 2;
             }
@@ -352,9 +363,10 @@ int rqb200_vae_finalize(rqb200_vae* h) {
     {
         const rqb200_vae_config& c = h->cfg;
         int r = c.resolution >> (c.n_levels - 1);
-        bool ok = c.mode == RQB200_MODE_FAST && c.ch % 128 == 0 && c.z_channels % 128 == 0 && c.embed_dim % 128 == 0 &&
+        bool ok = (c.mode & 0xff) == RQB200_MODE_FAST && c.ch % 128 == 0 && c.z_channels % 128 == 0 && c.embed_dim % 128 == 0 &&
                   c.out_ch == 3 && r > 0 && (r & (r - 1)) == 0;
         h->fast_ok = ok;
+        h->gn_fuse = !(c.mode & RQB200_VAE_NO_GN_FUSE);
         h->split = ok && h->t.find("decoder.conv_in.weight_lo") != h->t.end();
     }
     {

@@ -87,6 +87,8 @@ class RQVAE(Stage1Model):
         cfg.resolution, cfg.z_channels, cfg.embed_dim = dd["resolution"], dd["z_channels"], self.embed_dim
         cfg.in_channels, cfg.out_ch = dd["in_channels"], dd["out_ch"]
         cfg.codebook_size, cfg.depth, cfg.mode = self.quantizer.n_embed[0], self.code_shape[-1], mode
+        if os.environ.get("RQB200_GN_FUSE", "1") == "0":      # diagnostics: stand-alone GroupNorm statistics pass
+            cfg.mode |= 0x100
         handle = L.rqb200_vae_create(C.byref(cfg))
         if not handle:
             raise N.NativeError("rqb200_vae_create: " + L.rqb200_last_error().decode())

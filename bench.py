@@ -250,7 +250,11 @@ def parity_record(name, dev):
     from oracle import synth
     from tests.helpers import CodebookAux, build_ar, noise_tensor
     gold = os.path.join(ROOT, "tests", "golden")
-    g = torch.load(os.path.join(gold, "ar.pt"), weights_only=False)["ar"].get(name)
+    g, fixture = None, None
+    for fixture in ("ar.pt", "ar2.pt"):
+        g = torch.load(os.path.join(gold, fixture), weights_only=False)["ar"].get(name)
+        if g is not None:
+            break
     if g is None:
         return {"unavailable": "no reference fixture for " + name}
     with open(os.path.join(gold, "state_dict_layouts.json")) as f:
@@ -287,7 +291,7 @@ def parity_record(name, dev):
         free.append({"setting": {k: v for k, v in st.items()}, "first_divergent_step": first, "n_steps": n_tok})
     del model
     torch.cuda.empty_cache()
-    return {"reference_fixture": "tests/golden/ar.pt[%s] (B=%d, unmodified reference, fp32)" % (name, B),
+    return {"reference_fixture": "tests/golden/%s[%s] (B=%d, unmodified reference, fp32)" % (fixture, name, B),
             "teacher_forced": {"trajectory": {k: v for k, v in ref_run["setting"].items()}, "logit_std": std, "err_rms_over_std": float(err.pow(2).mean().sqrt()) / std,
                                "err_max_over_std": float(err.max()) / std, "max_err_vs_reference_logits": ref_err,
                                "greedy_flips": int(differ.sum()), "greedy_flips_outside_margin": int(outside.sum()),

@@ -60,6 +60,11 @@ int rqb200_device_count(void);
 int rqb200_rq_quantize(const float* x, const float* codebook, int64_t N, int K, int C, int D, int64_t* codes,
                        float* quant_list, float* residual_out, void* stream);
 
+/* One depth of RQBottleneck.get_soft_codes (quantizations.py:371-399): residual [N,C] f32 -> soft_out [N,K] = softmax(-d/temp) with
+ * d = VQEmbedding.compute_distances (:43-62); logits_out (nullable) [N,K] = -d/temp (what the stochastic variant samples from). */
+int rqb200_rq_soft_codes(const float* residual, const float* codebook, int64_t N, int K, int C, float temp, float* soft_out,
+                         float* logits_out, void* stream);
+
 /* RQBottleneck.embed_code (quantizations.py:297-311): out[n,:] = sum_d codebook[codes[n,d],:]  (order d=0..D-1). */
 int rqb200_rq_embed_sum(const int64_t* codes, const float* codebook, int64_t N, int D, int K, int C, float* out,
                         void* stream);

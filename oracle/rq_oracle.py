@@ -61,6 +61,19 @@ def rq_quantize(x, codebook, depth):
     return quants, torch.cat(codes, dim=-1)
 
 
+def rq_soft_codes(x, codebook, depth, temp=1.0):
+    """quantizations.py:371-399 (stochastic=False): per-depth softmax(-distances / temp) [..., D, K] and the argmin codes."""
+    residual = x.detach().clone()
+    softs, codes = [], []
+    for _ in range(depth):
+        d = vq_distances(residual, codebook)
+        softs.append(F.softmax(-d / temp, dim=-1).unsqueeze(-2))
+        idx = d.argmin(dim=-1)
+        residual.sub_(F.embedding(idx, codebook))
+        codes.append(idx.unsqueeze(-1))
+    return torch.cat(softs, dim=-2), torch.cat(codes, dim=-1)
+
+
 def embed_code(codes, codebook):
     """quantizations.py:297-311 -- sum over depth of codebook rows (cat then sum(-2)); rH=rW=1 so no reshape."""
     parts = [F.embedding(c, codebook) for c in torch.chunk(codes, codes.shape[-1], dim=-1)]

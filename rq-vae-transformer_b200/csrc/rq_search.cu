@@ -235,6 +235,66 @@ __global__ void rq_embed_kernel(const int64_t* __restrict__ codes, const float* 
     if (SUM) reinterpret_cast<float4*>(out + n * C)[c4] = acc;
 }
 
+// RQBottleneck.get_soft_codes' inner step (quantizations.py:381-383): for every residual vector r, all K distances
+// d_k = (||r||^2 + ||e_k||^2) - 2 r.e_k (the reference's addmm form) and soft = softmax(-d / temp) over the codebook.
+// Not a hot path (stage-2 soft targets): one CTA per vector, warp <-> codeword (coalesced 1 KB row reads out of L2), the K
+// negated-scaled distances staged in shared memory for the softmax.  logits_out (nullable) receives -d/temp itself (the
+// stochastic variant draws argmax(softmax(logits)/q) from it with rqb200_sample_logits).
+__global__ void __launch_bounds__(256)
+rq_soft_kernel(const float* __restrict__ r, const float* __restrict__ cb, int K, int C, float inv_temp, float* __restrict__ soft,
+               float* __restrict__ logits_out) {
+    extern __shared__ float rs_smem[];          // r[C] | z[K]
+    __shared__ float red[33];
+    float* rv = rs_smem;
+    float* z = rs_smem + C;
+    const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float rn = 0.f;
+    for (int c = t; c < C; c += 256) {
+        const float v = r[(int64_t)n * C + c];
+        rv[c] = v;
+        rn = fmaf(v, v, rn);
+    }
+    rn = block_sum(rn, red);                     // ||r||^2 (all threads)
+    __syncthreads();
+    for (int k = warp; k < K; k += 8) {
+        const float* e = cb + (int64_t)k * C;
+        float dot = 0.f, en = 0.f;
+        for (int c = lane * 4; c < C; c += 128) {
+            const float4 ev = *reinterpret_cast<const float4*>(e + c);
+            const float4 xv = *reinterpret_cast<const float4*>(rv + c);
+            dot = fmaf(xv.x, ev.x, dot); dot = fmaf(xv.y, ev.y, dot); dot = fmaf(xv.z, ev.z, dot); dot = fmaf(xv.w, ev.w, dot);
+            en = fmaf(ev.x, ev.x, en); en = fmaf(ev.y, ev.y, en); en = fmaf(ev.z, ev.z, en); en = fmaf(ev.w, ev.w, en);
+        }
+        dot = warp_sum(dot);
+        en = warp_sum(en);
+        if (lane == 0) z[k] = -(fmaf(-2.0f, dot, rn + en)) * inv_temp;
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int k = t; k < K; k += 256) m = fmaxf(m, z[k]);
+    m = block_max(m, red);
+    float sum = 0.f;
+    for (int k = t; k < K; k += 256) sum += expf(z[k] - m);
+    sum = block_sum(sum, red);
+    const float inv = 1.0f / sum;
+    for (int k = t; k < K; k += 256) {
+        const float zk = z[k];
+        soft[(int64_t)n * K + k] = expf(zk - m) * inv;
+        if (logits_out) logits_out[(int64_t)n * K + k] = zk;
+    }
+}
+
+int launch_rq_soft(const float* r, const float* cb, int64_t N, int K, int C, float temp, float* soft, float* logits_out,
+                   cudaStream_t st) {
+    if (N < 0 || K <= 0 || C <= 0 || C % 4 != 0 || !(temp > 0.f)) return fail(RQB200_EINVAL, "rq_soft_codes: bad shape / temperature");
+    if (N == 0) return 0;
+    const size_t smem = (size_t)(C + K) * sizeof(float);
+    if (smem > 200 * 1024) return fail(RQB200_EINVAL, "rq_soft_codes: codebook too large for the shared-memory staging (K + C <= 51200)");
+    RQB_ENSURE_SMEM(200 * 1024, rq_soft_kernel);
+    rq_soft_kernel<<<(unsigned)N, 256, smem, st>>>(r, cb, K, C, 1.0f / temp, soft, logits_out);
+    return check_launch("rq_soft_codes");
+}
+
 int launch_rq_embed(const int64_t* codes, const float* cb, int64_t N, int D, int K, int C, float* out, bool sum,
                     cudaStream_t st) {
     if (C % 4 != 0 || C > 4096 || N < 0 || D <= 0) return fail(RQB200_EINVAL, "rq_embed: bad shape");
@@ -271,6 +331,10 @@ int rqb200_rq_quantize(const float* x, const float* codebook, int64_t N, int K, 
 int rqb200_dbg_rq_quantize(int form, const float* x, const float* codebook, int64_t N, int K, int C, int D, int64_t* codes,
                            float* quant_list, float* residual_out, void* stream) {
     return rqb::launch_rq_quantize(x, codebook, N, K, C, D, codes, quant_list, residual_out, (cudaStream_t)stream, form);
+}
+int rqb200_rq_soft_codes(const float* residual, const float* codebook, int64_t N, int K, int C, float temp, float* soft_out,
+                         float* logits_out, void* stream) {
+    return rqb::launch_rq_soft(residual, codebook, N, K, C, temp, soft_out, logits_out, (cudaStream_t)stream);
 }
 int rqb200_rq_embed_sum(const int64_t* codes, const float* codebook, int64_t N, int D, int K, int C, float* out,
                         void* stream) {

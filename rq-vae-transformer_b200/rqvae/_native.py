@@ -63,6 +63,8 @@ def lib():
     L.rqb200_device_count.restype = C.c_int
     L.rqb200_rq_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
+    L.rqb200_rq_soft_codes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
     L.rqb200_rq_embed_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.rqb200_rq_embed_depth.argtypes = L.rqb200_rq_embed_sum.argtypes
     L.rqb200_sample_logits.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p,
@@ -115,7 +117,7 @@ def lib():
 
 
 EXPORTS = ["rqb200_last_error", "rqb200_version", "rqb200_device_count", "rqb200_rq_quantize", "rqb200_rq_embed_sum",
-           "rqb200_rq_embed_depth", "rqb200_sample_logits", "rqb200_ar_create", "rqb200_ar_destroy",
+           "rqb200_rq_embed_depth", "rqb200_rq_soft_codes", "rqb200_sample_logits", "rqb200_ar_create", "rqb200_ar_destroy",
            "rqb200_ar_workspace_bytes", "rqb200_ar_sample", "rqb200_ar_sample_span", "rqb200_ar_forward",
            "rqb200_ar_forward_workspace_bytes", "rqb200_ar_trace", "rqb200_ar_last_launches", "rqb200_vae_create",
            "rqb200_vae_destroy", "rqb200_vae_set_tensor", "rqb200_vae_finalize", "rqb200_vae_workspace_bytes",

@@ -52,3 +52,18 @@ def sample_logits(logits, temperature=1.0, top_k=None, top_p=None, q=None):
                                              N.stream_ptr(logits.device)), "sample_logits")
     N.launch_count["total"] += 1
     return out
+
+
+def rq_soft(residual, codebook, temp=1.0, want_logits=False):
+    """residual [n,C] -> softmax(-distances / temp) [n,K] (and optionally the logits -d/temp)"""
+    r = _prep(residual, torch.float32)
+    cb = _prep(codebook, torch.float32)
+    n, C = r.shape
+    K = cb.shape[0]
+    soft = torch.empty(n, K, dtype=torch.float32, device=r.device)
+    logits = torch.empty(n, K, dtype=torch.float32, device=r.device) if want_logits else None
+    with torch.cuda.device(r.device):
+        N.check(N.lib().rqb200_rq_soft_codes(N.ptr(r), N.ptr(cb), n, K, C, float(temp), N.ptr(soft), N.ptr(logits),
+                                             N.stream_ptr(r.device)), "rq_soft_codes")
+    N.launch_count["total"] += 1 if n else 0
+    return (soft, logits) if want_logits else soft

@@ -122,6 +122,34 @@ class RQBottleneck(nn.Module):
         return torch.mean(torch.stack([(x - q.detach()).pow(2.0).mean() for q in quant_list]))
 
     @torch.no_grad()
+    def get_soft_codes(self, x, temp=1.0, stochastic=False):
+        """quantizations.py:371-399: per depth softmax(-distances/temp) over the codebook ([B,h,w,D,K]) and the codes taken along
+        the way -- argmin (then identical to ``quantize``) or, stochastic, one multinomial draw per vector from the soft code."""
+        x = self.to_code_shape(x)
+        B, h, w, C = x.shape
+        depth = self.code_shape[-1]
+        cb = self._shared_table()
+        flat = x.reshape(-1, C).float().contiguous()
+        softs, codes = [], []
+        if not stochastic:
+            ql, code = nb.rq_quantize(flat, cb, depth)
+            for d in range(depth):
+                softs.append(nb.rq_soft(flat if d == 0 else flat - ql[d - 1], cb, temp))
+            codes = code
+        else:
+            res = flat.clone()
+            for d in range(depth):
+                soft, logits = nb.rq_soft(res, cb, temp, want_logits=True)
+                q = torch.empty_like(soft).exponential_(1)        # the draw torch.multinomial(soft, 1) makes
+                idx = nb.sample_logits(logits, 1.0, None, None, q=q)
+                res = res - nb.rq_embed(idx.reshape(-1, 1), cb, summed=True)
+                softs.append(soft)
+                codes.append(idx.unsqueeze(-1))
+            codes = torch.cat(codes, -1)
+        soft = torch.stack(softs, dim=1).reshape(B, h, w, depth, -1)
+        return soft, codes.reshape(B, h, w, depth)
+
+    @torch.no_grad()
     def embed_code(self, code):
         """quantizations.py:297-311"""
         assert code.shape[1:] == self.code_shape

@@ -236,4 +236,6 @@ class RQVAE(Stage1Model):
 
     @torch.no_grad()
     def get_soft_codes(self, xs, temp=1.0, stochastic=False):
-        raise NotImplementedError("rqb200: get_soft_codes (stage-2 training targets) is out of scope")
+        """rqvae.py:97-103"""
+        z_e = self.encode(xs)
+        return self.quantizer.get_soft_codes(z_e, temp=temp, stochastic=stochastic)

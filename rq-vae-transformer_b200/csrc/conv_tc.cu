@@ -48,6 +48,52 @@ constexpr int CT_A_BYTES = 128 * 64 * 2;
 // PASSES == 1: single fp16 product.  PASSES == 3: split-fp16 ("fp16x3") -- both operands are carried as hi + lo fp16 pairs and
 // the accumulator receives A_hi W_hi + A_lo W_hi + A_hi W_lo (the dropped A_lo W_lo term is ~2^-22 relative): fp32-class
 // products on the fp16 tensor pipe, which is what keeps 60 chained convs inside the 1e-3 pixel tolerance.
+// GroupNorm partial statistics of one 16-channel chunk of a warp's 32 pixels: NV = 2 * (16 / CG) values (the sums, then the sums
+// of squares, of the chunk's 16 / CG groups) are formed per thread and reduced over the 32 lanes with a transpose-reduce
+// (log2(NV) halving steps, then plain butterfly steps): NV + 1 shuffles of depth 5 instead of 5 * NV.  On return `tot` is the total
+// of value index `vidx` and `writer` marks the one lane per value that stores it.
+template <int CG>
+__device__ __forceinline__ void gn_chunk_stats(const float (&wv)[16], bool valid, int lane, float& tot, int& vidx, bool& writer) {
+    constexpr int NG = 16 / CG, NV = 2 * NG;
+    float vals[NV];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < CG; i++) {
+            const float x = valid ? wv[g * CG + i] : 0.f;
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+        }
+        vals[g] = s1;
+        vals[NG + g] = s2;
+    }
+    int n = NV;
+    vidx = 0;
+    int keep_mask = 31;                         // lanes that end up holding identical totals differ only in these bits
+#pragma unroll
+    for (int S = 16; S >= 1; S >>= 1) {
+        if (n > 1) {
+            const int half = n >> 1;
+            const bool up = (lane & S) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; i++)
+                if (i < half) {
+                    const float send = up ? vals[i] : vals[i + half];
+                    const float keep = up ? vals[i + half] : vals[i];
+                    vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+                }
+            vidx += up ? half : 0;
+            keep_mask &= ~S;
+            n = half;
+        } else {
+            vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], S);
+        }
+    }
+    tot = vals[0];
+    writer = (lane & keep_mask) == 0;
+}
+
 template <int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -209,26 +255,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (p.gn_part != nullptr) {
                         // this warp's 32 pixels belong to one image (TW*TH >= 32, checked by the host); cg = 4 | 8 | 16 channels
-                        const int cg = p.Cout >> 5, ngr = 16 / cg;
+                        const int cg = p.Cout >> 5;
                         const int wpi = (p.TW * p.TH) >> 5;                      // warps (32-pixel chunks) per image within a tile
                         const int chunk = (ty * p.tiles_x + tx) * wpi + (q % wpi);
                         const int bw = tb * p.NB + (q * 32) / (p.TW * p.TH);      // image of this warp
-#pragma unroll
-                        for (int gi = 0; gi < 4; gi++) {
-                            if (gi < ngr) {                                       // (warp-uniform)
-                                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                                for (int i = 0; i < 16; i++)
-                                    if (i / cg == gi && valid) { s1 += wv[i]; s2 = fmaf(wv[i], wv[i], s2); }
-                                s1 = warp_sum(s1);
-                                s2 = warp_sum(s2);
-                                if (lane == 0 && bw < p.B) {
-                                    double* dst = p.gn_part + (((int64_t)bw * p.gn_chunks + chunk) * 32 + (n0 / cg + gi)) * 2;
-                                    dst[0] = (double)s1;
-                                    dst[1] = (double)s2;
-                                }
-                            }
-                        }
+                        float tot;
+                        int vidx;
+                        bool writer;
+                        if (cg == 4) gn_chunk_stats<4>(wv, valid, lane, tot, vidx, writer);
+                        else if (cg == 8) gn_chunk_stats<8>(wv, valid, lane, tot, vidx, writer);
+                        else gn_chunk_stats<16>(wv, valid, lane, tot, vidx, writer);
+                        const int ngr = 16 / cg;
+                        if (writer && bw < p.B)                                    // vidx < ngr: sum of group vidx; else sum of squares
+                            p.gn_part[(((int64_t)bw * p.gn_chunks + chunk) * 32 + (n0 / cg + (vidx % ngr))) * 2 + (vidx / ngr)] = (double)tot;
                     }
                 }
             }

@@ -46,6 +46,8 @@ extern "C" {
 #define RQB200_AR_SHALLOW_RING 16       /* half-depth GEMM rings: two GEMM CTAs of consecutive launches share an SM        */
 #define RQB200_AR_SEQUENTIAL_PREFILL 32 /* prefill the prefix token by token with the single-step graph (the prefill oracle) */
 #define RQB200_AR_BATCHED_DEEP_RING 64  /* large-M passes (prefill / forward) keep the deep ring: one CTA per SM                  */
+#define RQB200_AR_ATTN_ONE_WARP 256    /* body attention: one warp per (b, head) (round-1/2 form) instead of four               */
+#define RQB200_AR_TRACE_WEIGHTS 512    /* with TRACE: GEMM stamp 0 = prefetched weight tiles landed (instead of kernel entry)    */
 #define RQB200_AR_BATCHED_STREAMER 128  /* large-M passes through the weight-streaming GEMM instead of the persistent rows GEMM    */
 
 const char* rqb200_last_error(void);

@@ -11,7 +11,8 @@ from rqvae import _native as N  # noqa: E402
 L = N.lib()
 ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
 NAMES = {0: "PDL chain, empty kernels", 1: "PDL chain, 16 KB L2 round trip / CTA", 2: "persistent, grid barrier",
-         3: "persistent, point-to-point flags"}
+         3: "persistent, point-to-point flags", 4: "PDL chain, 16 KB, loads before stores"}
+MODES = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4]
 
 
 def run(mode, ctas, threads, smem, fan, n=400, reps=10):
@@ -20,7 +21,7 @@ def run(mode, ctas, threads, smem, fan, n=400, reps=10):
     return us.value
 
 
-for mode in (0, 1, 2, 3):
+for mode in MODES:
     for ctas, threads, smem in ((144, 192, 0), (144, 192, 100 << 10), (144, 192, 200 << 10), (64, 384, 0), (288, 128, 0), (444, 128, 0)):
         for fan in ((1, 8, 32) if mode else (1,)):
             try:

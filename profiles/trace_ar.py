@@ -7,7 +7,7 @@ usage: python profiles/trace_ar.py [model] [B]   -> gpurun_out/trace_ar_<model>.
 import os
 import sys
 
-os.environ["RQB200_TRACE"] = "1"
+os.environ.setdefault("RQB200_TRACE", "1")      # "2": GEMM stamp 0 = prefetched weights landed (instead of entry)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "rq-vae-transformer_b200"))

@@ -106,6 +106,7 @@ ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ parti
     }
     if (xn) {
         const float mean = block_sum(s, red) / (float)E;
+        if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[2] = tc::gtimer();      // every load has landed, first reduction done
         float q = 0.f;
 #pragma unroll
         for (int k = 0; k < 3; k++)
@@ -124,8 +125,64 @@ ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ parti
                 reinterpret_cast<uint2*>(xn + (int64_t)b * E)[e4] = pk;
             }
         }
+        if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[3] = tc::gtimer();
+    } else {
+        TR_OUT(tr);
     }
-    TR_OUT(tr);
+}
+
+// The batched passes' LayerNorm (prefill / teacher-forced forward: thousands of rows, no split-K partials): one WARP per row, the
+// row in registers between the statistics and the normalisation, rows grid-strided over 8-warp CTAs.  (ln_reduce_kernel's
+// one-384-thread-CTA-per-row form is built for 64 rows on 64 SMs; on 4096+ rows it ran at a tenth of the HBM rate.)
+// x_out (nullable) = x_in (+ extra row); xn (nullable) = LayerNorm(x) in 16-bit.  NV = float4 chunks per lane (E <= 128 * NV).
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_rows_kernel(const float* __restrict__ x_in, const float* __restrict__ extra, float* __restrict__ x_out, const float* __restrict__ g,
+               const float* __restrict__ be, h16* __restrict__ xn, int64_t M, int E, int bf) {
+    const int lane = threadIdx.x & 31;
+    const int E4 = E >> 2;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * 8) {
+        const float4* xr = reinterpret_cast<const float4*>(x_in + row * E);
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const int e4 = lane + 32 * k;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e4 < E4) v[k] = xr[e4];
+        }
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const int e4 = lane + 32 * k;
+            if (e4 < E4) {
+                if (extra) { const float4 t = reinterpret_cast<const float4*>(extra)[e4]; v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w; }
+                if (x_out) reinterpret_cast<float4*>(x_out + row * E)[e4] = v[k];
+                s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+            }
+        }
+        if (xn) {
+            const float mean = warp_sum(s) / (float)E;
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < NV; k++)
+                if (lane + 32 * k < E4) {
+                    const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+                    q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+                }
+            const float rstd = rsqrtf(warp_sum(q) / (float)E + 1e-5f);
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                const int e4 = lane + 32 * k;
+                if (e4 < E4) {
+                    const float4 gg = reinterpret_cast<const float4*>(g)[e4], bb = reinterpret_cast<const float4*>(be)[e4];
+                    uint2 pk;
+                    pk.x = pack_h16x2((v[k].x - mean) * rstd * gg.x + bb.x, (v[k].y - mean) * rstd * gg.y + bb.y, bf);
+                    pk.y = pack_h16x2((v[k].z - mean) * rstd * gg.z + bb.z, (v[k].w - mean) * rstd * gg.w + bb.w, bf);
+                    reinterpret_cast<uint2*>(xn + row * E)[e4] = pk;
+                }
+            }
+        }
+    }
 }
 
 // h = 16-bit(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K); 4 elements per thread, all partial loads in flight
@@ -285,6 +342,136 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[3] = tc::gtimer();
 }
 
+// Four warps per (b, head) -- the body stack's form.  The cached K / V rows [0, t) are staged in shared memory by cp.async (16 B
+// per request, every request of the CTA in flight at once, issued right after the dependency resolves and overlapped with the
+// q/k/v split-K reduction): the whole KV read of a step is ONE memory round trip instead of two (K, then V) serialised per 64 rows
+// in one warp's registers.  Rows are 128 B with the 16 B chunks XOR-swizzled by (row & 7): conflict-free for the score pass
+// (a lane pair per row, 4 chunks each) and for the output pass (a warp per row, lane <-> dims (2*lane, 2*lane+1)).
+// Softmax statistics go through shared memory; warp w adds the rows j = w (mod 4) in cache order and the four partial outputs
+// are summed in warp order -> run-to-run deterministic.  q/k/v bits as in attn_fast_kernel (same reduction order).
+// 11 CTAs per SM (40 registers, 19.6 KB at 64 rows): the 1536 (b, head) pairs of the 1.4B model at B = 64 are one wave.
+constexpr int AF2_MAXROWS = 320;
+static size_t attn2_smem(int rows) { return (size_t)rows * 256 + ((size_t)rows + 64 * 3 + 4 * 64 + 8) * sizeof(float); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__global__ void __launch_bounds__(128, 11)
+attn_fast2_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, h16* __restrict__ kc, h16* __restrict__ vc,
+                  h16* __restrict__ att, int B, int E, int nh, int Tmax, int rows, const int* __restrict__ t_ptr, int t_host, int bf,
+                  long long* tr) {
+    extern __shared__ __align__(128) uint8_t af2_smem[];
+    uint8_t* Ks = af2_smem;                                   // [rows][128 B], chunk c of row j at ((c ^ (j & 7)) << 4)
+    uint8_t* Vs = Ks + (size_t)rows * 128;
+    float* ps = reinterpret_cast<float*>(Vs + (size_t)rows * 128);   // scores, then exp(score - max)
+    float* qs = ps + rows;                // q, k_new, v_new (16-bit-rounded), 64 floats each
+    float* kn = qs + 64;
+    float* vn = kn + 64;
+    float* ov = vn + 64;                  // [4][64] partial outputs
+    float* red = ov + 256;                // [0..3] warp maxima, [4..7] warp sums
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    tc::pdl_launch_dependents();
+    TR_IN(tr);
+    tc::pdl_wait();
+    TR_DEP(tr);
+    const int b = blockIdx.x / nh, h = blockIdx.x % nh;
+    const int t = t_ptr ? *t_ptr : t_host;
+    h16* kb = kc + ((int64_t)(b * nh + h) * Tmax) * 64;
+    h16* vb = vc + ((int64_t)(b * nh + h) * Tmax) * 64;
+    {
+        const uint32_t ks = tc::smem_u32(Ks), vs = tc::smem_u32(Vs);
+        for (int i = threadIdx.x; i < t * 8; i += 128) {
+            const int j = i >> 3, c = i & 7;
+            const uint32_t off = (uint32_t)j * 128u + (uint32_t)((c ^ (j & 7)) << 4);
+            cp_async16(ks + off, kb + (int64_t)j * 64 + c * 8);
+            cp_async16(vs + off, vb + (int64_t)j * 64 + c * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ---- q / k / v of the new token: warp 0 -> q, warp 1 -> k, warp 2 -> v (value = bias + p0 + p1 + ..., split order)
+    if (w < 3) {
+        const int c = h * 64 + 2 * lane;
+        float2 a = make_float2(bqkv[w * E + c], bqkv[w * E + c + 1]);
+#pragma unroll 4
+        for (int s = 0; s < S; s++) {
+            const float2 pp = *reinterpret_cast<const float2*>(part + ((int64_t)s * B + b) * 3 * E + w * E + c);
+            a.x += pp.x; a.y += pp.y;
+        }
+        const uint32_t a2 = pack_h16x2(a.x, a.y, bf);
+        const float2 af = unpack_h16x2(a2, bf);
+        float* dst = w == 0 ? qs : (w == 1 ? kn : vn);
+        dst[2 * lane] = af.x;
+        dst[2 * lane + 1] = af.y;
+        if (w == 1) *reinterpret_cast<uint32_t*>(kb + (int64_t)t * 64 + 2 * lane) = a2;
+        if (w == 2) *reinterpret_cast<uint32_t*>(vb + (int64_t)t * 64 + 2 * lane) = a2;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const float s_new = warp_sum(qs[2 * lane] * kn[2 * lane] + qs[2 * lane + 1] * kn[2 * lane + 1]) * 0.125f;
+    float m = -INFINITY;
+    {
+        const int half = threadIdx.x & 1;
+        for (int j0 = 0; j0 < t; j0 += 64) {
+            const int j = j0 + (threadIdx.x >> 1);
+            float acc = 0.f;
+            if (j < t) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int c = half * 4 + i;
+                    const uint4 k4 = *reinterpret_cast<const uint4*>(Ks + (size_t)j * 128 + ((c ^ (j & 7)) << 4));
+                    const float4 qa = *reinterpret_cast<const float4*>(qs + c * 8), qb = *reinterpret_cast<const float4*>(qs + c * 8 + 4);
+                    float2 kk = unpack_h16x2(k4.x, bf);
+                    acc = fmaf(qa.x, kk.x, acc); acc = fmaf(qa.y, kk.y, acc);
+                    kk = unpack_h16x2(k4.y, bf);
+                    acc = fmaf(qa.z, kk.x, acc); acc = fmaf(qa.w, kk.y, acc);
+                    kk = unpack_h16x2(k4.z, bf);
+                    acc = fmaf(qb.x, kk.x, acc); acc = fmaf(qb.y, kk.y, acc);
+                    kk = unpack_h16x2(k4.w, bf);
+                    acc = fmaf(qb.z, kk.x, acc); acc = fmaf(qb.w, kk.y, acc);
+                }
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc *= 0.125f;
+            if (j < t) {
+                if (half == 0) ps[j] = acc;
+                m = fmaxf(m, acc);
+            }
+        }
+    }
+    m = warp_max(m);
+    if (lane == 0) red[w] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), s_new);
+    if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[2] = tc::gtimer();      // scores done
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < t; j += 128) {
+        const float e = __expf(ps[j] - m);
+        ps[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[4 + w] = sum;
+    __syncthreads();
+    const float e_new = __expf(s_new - m);
+    const float inv = 1.0f / ((((red[4] + red[5]) + red[6]) + red[7]) + e_new);
+    float2 o = w == 0 ? make_float2(e_new * vn[2 * lane], e_new * vn[2 * lane + 1]) : make_float2(0.f, 0.f);
+    for (int j = w; j < t; j += 4) {
+        const uint32_t v2 = *reinterpret_cast<const uint32_t*>(Vs + (size_t)j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + ((lane & 3) << 2));
+        const float2 vv = unpack_h16x2(v2, bf);
+        const float pj = ps[j];
+        o.x = fmaf(pj, vv.x, o.x);
+        o.y = fmaf(pj, vv.y, o.y);
+    }
+    ov[w * 64 + 2 * lane] = o.x;
+    ov[w * 64 + 2 * lane + 1] = o.y;
+    __syncthreads();
+    if (w == 0) {
+        const float ox = ((ov[2 * lane] + ov[64 + 2 * lane]) + ov[128 + 2 * lane]) + ov[192 + 2 * lane];
+        const float oy = ((ov[2 * lane + 1] + ov[64 + 2 * lane + 1]) + ov[128 + 2 * lane + 1]) + ov[192 + 2 * lane + 1];
+        *reinterpret_cast<uint32_t*>(att + (int64_t)b * E + h * 64 + 2 * lane) = pack_h16x2(ox * inv, oy * inv, bf);
+    }
+    if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[3] = tc::gtimer();
+}
+
 // Causal attention over a whole prefix in one launch (batched prefill / teacher-forced forward).  qkv [M, 3E] 16-bit (bias already
 // added by the GEMM epilogue), row of (group g, token t) = t * G + g  (token-major: the rows of one token are contiguous, like the
 // single-step buffers).  One CTA per (group, head); the group's K and V rows are staged in shared memory (row stride 66 elements:
@@ -436,11 +623,11 @@ struct ArFast {
     cudaGraphExec_t graphs[G_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     int64_t n_nodes[G_COUNT] = {0, 0, 0, 0};   // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
-    bool use_graph = true, use_pdl = true, deep = true, l2pf = false, batched_prefill = true, batched_deep = false, batched_streamer = false;
+    bool use_graph = true, use_pdl = true, attn4 = true, deep = true, l2pf = false, batched_prefill = true, batched_deep = false, batched_streamer = false;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
     int n_sm = 148;
     // diagnostic stage trace (cfg.flags & RQB200_AR_TRACE)
-    bool trace = false;
+    bool trace = false, trace_w = false;
     mutable long long* tr_base = nullptr;
     mutable int tr_next = 0;
     mutable std::vector<std::string> tr_names;
@@ -524,18 +711,46 @@ static int gemm(const ArFast& f, const char* name, const CUtensorMap& tw, const 
     p.bias = bias; p.bias_scale = bias_scale; p.out = out; p.partial = partial;
     p.residual = residual; p.ld_res = ld_res; p.res_row_ptr = res_row_ptr; p.res_row_stride = res_row_stride;
     p.trace = tr_slot(f, name);
+    p.trace_w = f.trace_w ? 1 : 0;
     return launch_gemm_tc(tw, tx, p, f.use_pdl, st);
 }
 
 static int ln(const ArFast& f, const char* name, int rows, const float* x_in, const float* partial, int S, const float* bias,
               const float* extra, float* x_out, const float* g, const float* be, h16* xn, cudaStream_t st) {
+    const int E = f.cfg.embed_dim;
+    if (rows >= 512 && S == 0 && bias == nullptr && x_in != nullptr) {        // batched passes: warp per row
+        const dim3 grid((unsigned)std::min<int64_t>(ceil_div(rows, 8), (int64_t)f.n_sm * 8));
+        const int nv = ceil_div(E, 128);
+#define RQB_LN_ROWS(NV) launch_pdl(ln_rows_kernel<NV>, grid, dim3(256), (size_t)0, st, false, x_in, extra, x_out, g, be, xn, (int64_t)rows, E, f.bf)
+        if (nv <= 8) return RQB_LN_ROWS(8);
+        if (nv <= 12) return RQB_LN_ROWS(12);
+        if (nv <= 20) return RQB_LN_ROWS(20);
+        return RQB_LN_ROWS(36);
+#undef RQB_LN_ROWS
+    }
     return launch_pdl(ln_reduce_kernel, dim3((unsigned)rows), dim3(384), (size_t)0, st, f.use_pdl, x_in, partial, S, bias, extra, x_out, g,
-                      be, xn, rows, f.cfg.embed_dim, f.bf, tr_slot(f, name));
+                      be, xn, rows, E, f.bf, tr_slot(f, name));
 }
 
 static int attn(const ArFast& f, FastWs& ws, const float* bqkv, h16* kc, h16* vc, int Tmax, const int* t_ptr, int t_host,
                 cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
+    if (f.attn4 && Tmax >= 16 && Tmax - 1 <= AF2_MAXROWS) {          // the body stack: four warps per (b, head)
+        const int rows = Tmax - 1;                                   // cached rows a step can read (row t is the new token)
+        RQB_ENSURE_SMEM(attn2_smem(AF2_MAXROWS), attn_fast2_kernel);
+        {   // 11 CTAs x 19.6 KB need the largest shared-memory carve-out (L1 is not used by this kernel)
+            static std::atomic<uint64_t> carve{0};
+            int dev = 0;
+            RQB_CUDA(cudaGetDevice(&dev));
+            if (!(carve.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+                RQB_CUDA(cudaFuncSetAttribute(attn_fast2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                carve.fetch_or(1ull << (dev & 63), std::memory_order_release);
+            }
+        }
+        return launch_pdl(attn_fast2_kernel, dim3((unsigned)(f.B * c.n_head)), dim3(128), attn2_smem(rows), st, f.use_pdl,
+                          (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, rows, t_ptr, t_host,
+                          f.bf, tr_slot(f, "attn"));
+    }
     const size_t smem = (size_t)(4 * ((Tmax + 31) & ~31)) * sizeof(float);
     return launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(f.B * c.n_head, 4)), dim3(128), smem, st, f.use_pdl,
                       (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, t_ptr, t_host, f.bf,
@@ -678,8 +893,10 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     f->use_graph = !(cfg.flags & RQB200_AR_NO_GRAPH);
     f->use_pdl = !(cfg.flags & RQB200_AR_NO_PDL);
     f->trace = (cfg.flags & RQB200_AR_TRACE) != 0;
+    f->trace_w = (cfg.flags & RQB200_AR_TRACE_WEIGHTS) != 0;
     f->l2pf = (cfg.flags & RQB200_AR_L2_PREFETCH) != 0;
     f->deep = !(cfg.flags & RQB200_AR_SHALLOW_RING);
+    f->attn4 = !(cfg.flags & RQB200_AR_ATTN_ONE_WARP);
     f->batched_prefill = !(cfg.flags & RQB200_AR_SEQUENTIAL_PREFILL);
     f->batched_deep = (cfg.flags & RQB200_AR_BATCHED_DEEP_RING) != 0;
     f->batched_streamer = (cfg.flags & RQB200_AR_BATCHED_STREAMER) != 0;

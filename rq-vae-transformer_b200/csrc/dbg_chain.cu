@@ -6,6 +6,7 @@
 //   mode 1  PDL chain, every CTA reads 16 KB written by ANOTHER CTA of the previous kernel and writes 16 KB (L2 round trip)
 //   mode 2  one persistent kernel, the same data flow, stages separated by a grid-wide barrier (release/acquire counter)
 //   mode 3  one persistent kernel, the same data flow, every CTA waits only for the epoch flags of the `fan` CTAs it reads from
+//   mode 4  mode 1 with all of a thread's loads in flight before its first store (threads * 8 float4 >= 16 KB)
 // Result: microseconds per stage.  tests/test_gpu_tc.py only checks that it runs; profiles/bench_chain.py prints the table.
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -27,11 +28,33 @@ __device__ __forceinline__ void chain_stage_work(const float* __restrict__ in, f
     if (acc.x == -1.f) out[0] = acc.y;                    // keep the loads alive
 }
 
+// the same data flow with every load of a thread in flight before its first store (one round trip per stage instead of one per
+// loop iteration): the floor of a well-formed stage
+__device__ __forceinline__ void chain_stage_work_mlp(const float* __restrict__ in, float* __restrict__ out, int src_cta, int fan, int ctas) {
+    const int per = CH_WORDS / 4 / fan;
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = threadIdx.x + k * blockDim.x;
+        if (i < CH_WORDS / 4) {
+            const int pr = (src_cta + i / per) % ctas;
+            v[k] = __ldcg(reinterpret_cast<const float4*>(in + (size_t)pr * CH_WORDS) + i);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = threadIdx.x + k * blockDim.x;
+        if (i < CH_WORDS / 4)
+            __stcg(reinterpret_cast<float4*>(out + (size_t)blockIdx.x * CH_WORDS) + i, make_float4(v[k].x + 1.f, v[k].y, v[k].z, v[k].w));
+    }
+}
+
 __global__ void chain_pdl_kernel(const float* in, float* out, int work, int fan) {
     // (dynamic shared memory is requested by the launch only to control how many CTAs fit on an SM; it is never touched)
     tc::pdl_launch_dependents();
     tc::pdl_wait();
-    if (work) chain_stage_work(in, out, (blockIdx.x * 7 + 1) % gridDim.x, fan, gridDim.x);
+    if (work == 1) chain_stage_work(in, out, (blockIdx.x * 7 + 1) % gridDim.x, fan, gridDim.x);
+    else if (work == 4) chain_stage_work_mlp(in, out, (blockIdx.x * 7 + 1) % gridDim.x, fan, gridDim.x);
 }
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -81,7 +104,7 @@ __global__ void chain_persistent_kernel(float* a, float* b, int n_stages, int fa
 extern "C" int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, int smem_bytes, int fan, int reps, void* workspace,
                                 size_t workspace_bytes, float* us_per_stage) {
     using namespace rqb;
-    if (mode < 0 || mode > 3 || n_stages < 1 || ctas < 1 || threads < 32 || threads > 1024 || fan < 1 || fan > 32 || reps < 1 ||
+    if (mode < 0 || mode > 4 || n_stages < 1 || ctas < 1 || threads < 32 || threads > 1024 || fan < 1 || fan > 32 || reps < 1 ||
         (CH_WORDS / 4) % fan != 0)
         return fail(RQB200_EINVAL, "dbg_chain: bad arguments");
     const size_t need = (size_t)2 * ctas * CH_WORDS * sizeof(float) + 4096 + (size_t)ctas * 4;
@@ -97,7 +120,7 @@ extern "C" int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, i
     RQB_CUDA(cudaEventCreate(&e0));
     RQB_CUDA(cudaEventCreate(&e1));
     float ms = 0.f;
-    if (mode <= 1) {
+    if (mode <= 1 || mode == 4) {
         if (smem_bytes > 48 * 1024)
             RQB_CUDA(cudaFuncSetAttribute(chain_pdl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         cudaGraph_t g = nullptr;

@@ -153,7 +153,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
+    uint64_t* xfull = full + STAGES;              // activations land on their own barrier (weights: full[])
+    uint64_t* empty = xfull + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
@@ -167,10 +168,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
     tc::pdl_launch_dependents();             // let the next kernel of the chain start its own weight prefetch
     if (warp == 0 && lane == 0) {
-        if (tr) p.trace[0] = tc::gtimer();
+        if (tr && !p.trace_w) p.trace[0] = tc::gtimer();
         tc::prefetch_tmap(&tmW);
         tc::prefetch_tmap(&tmX);
-        for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&xfull[s], 1); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
     }
@@ -187,29 +188,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             // streamed once (M <= 256: evict first) or shared by every row chunk of a large-M launch (keep in L2)
             const uint64_t w_hint = gridDim.y > 1 ? tc::L2_EVICT_LAST : tc::L2_EVICT_FIRST;
             for (int i = 0; i < pre; i++) {
-                tc::mbar_expect_tx(&full[i], STAGE_BYTES);
+                tc::mbar_expect_tx(&full[i], GT_A_BYTES);
                 tc::tma_load_2d(smem + i * STAGE_BYTES, &tmW, &full[i], (kb0 + i) * 64, tile * 128, w_hint);
             }
             if (p.l2pf)
                 for (int i = pre; i < nkb; i++) tc::tma_prefetch_2d(&tmW, (kb0 + i) * 64, tile * 128);
             tc::pdl_wait();
             if (tr) p.trace[1] = tc::gtimer();
-            for (int i = 0; i < pre; i++)
-                tc::tma_load_2d(smem + i * STAGE_BYTES + GT_A_BYTES, &tmX, &full[i], (kb0 + i) * 64, m0, tc::L2_EVICT_LAST);
+            for (int i = 0; i < pre; i++) {
+                tc::mbar_expect_tx(&xfull[i], B_BYTES);
+                tc::tma_load_2d(smem + i * STAGE_BYTES + GT_A_BYTES, &tmX, &xfull[i], (kb0 + i) * 64, m0, tc::L2_EVICT_LAST);
+            }
             for (int i = pre; i < nkb; i++) {
                 const int s = i % STAGES;
                 tc::mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
-                tc::mbar_expect_tx(&full[s], STAGE_BYTES);
+                tc::mbar_expect_tx(&full[s], GT_A_BYTES);
                 tc::tma_load_2d(smem + s * STAGE_BYTES, &tmW, &full[s], (kb0 + i) * 64, tile * 128, w_hint);
-                tc::tma_load_2d(smem + s * STAGE_BYTES + GT_A_BYTES, &tmX, &full[s], (kb0 + i) * 64, m0, tc::L2_EVICT_LAST);
+                tc::mbar_expect_tx(&xfull[s], B_BYTES);
+                tc::tma_load_2d(smem + s * STAGE_BYTES + GT_A_BYTES, &tmX, &xfull[s], (kb0 + i) * 64, m0, tc::L2_EVICT_LAST);
             }
         }
     } else if (warp == 1) {
         // ---- MMA issuer
         const uint32_t idesc = tc::umma_idesc(128, BN, p.fmt);
+        if (tr && p.trace_w) {
+            // diagnostic: when did the weight tiles requested ahead of the dependency land?  (replaces the entry stamp)
+            for (int i = 0; i < (nkb < STAGES ? nkb : STAGES); i++) tc::mbar_wait(&full[i], 0);
+            if (lane == 0) p.trace[0] = tc::gtimer();
+        }
         for (int i = 0; i < nkb; i++) {
             const int s = i % STAGES;
             tc::mbar_wait(&full[s], (i / STAGES) & 1);
+            tc::mbar_wait(&xfull[s], (i / STAGES) & 1);
             tc::tc_fence_after();
             if (lane == 0) {
                 const uint32_t a = tc::smem_u32(smem + s * STAGE_BYTES), b = a + GT_A_BYTES;
@@ -247,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
 template <int BN, int STAGES>
 static int launch_gemm_tc_t(const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmTcParams& p, bool pdl, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (GT_A_BYTES + BN * 128) + 1024 + 256;
+    constexpr size_t smem = (size_t)STAGES * (GT_A_BYTES + BN * 128) + 1024 + 512;
     RQB_ENSURE_SMEM(smem, gemm_tc_kernel<BN, STAGES>);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ceil_div(p.N_out, 128) * p.splits), (unsigned)ceil_div(p.B, BN));

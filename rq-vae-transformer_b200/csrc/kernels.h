@@ -85,6 +85,7 @@ struct GemmTcParams {
     int64_t ld_out;
     float* partial;               // GT_PARTIAL: [splits][B][N_out] f32 (no bias)
     long long* trace;             // diagnostics, nullable: 4 globaltimer stamps of CTA 0 (entry, dependency resolved, accumulator ready, done)
+    int trace_w;                  // diagnostics: stamp 0 = the weight tiles requested ahead of the dependency have landed (instead of entry)
 };
 inline int gemm_tc_bn(int B) { return B <= 16 ? 16 : B <= 32 ? 32 : B <= 64 ? 64 : B <= 128 ? 128 : 256; }
 int make_tmap_weight(CUtensorMap* out, const void* W, int N_out, int K);

@@ -11,6 +11,7 @@ OK, EINVAL, ECUDA, ENODEV, EWORKSPACE, ESTATE = 0, -1, -2, -3, -4, -5
 F32, BF16, F16 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
 AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_BATCHED_DEEP_RING, AR_BATCHED_STREAMER = 1, 2, 4, 8, 16, 32, 64, 128
+AR_ATTN_ONE_WARP, AR_TRACE_WEIGHTS = 256, 512
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 c_f32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p
@@ -167,12 +168,14 @@ def ar_engine_options():
     flags = 0
     flags |= AR_NO_GRAPH if env("RQB200_NO_GRAPH", "0") == "1" else 0
     flags |= AR_NO_PDL if env("RQB200_NO_PDL", "0") == "1" else 0
-    flags |= AR_TRACE if env("RQB200_TRACE", "0") == "1" else 0
+    flags |= AR_TRACE if env("RQB200_TRACE", "0") in ("1", "2") else 0
+    flags |= AR_TRACE_WEIGHTS if env("RQB200_TRACE", "0") == "2" else 0
     flags |= AR_L2_PREFETCH if env("RQB200_GEMM_L2PF", "0") == "1" else 0
     flags |= AR_SHALLOW_RING if env("RQB200_GEMM_SHALLOW", "0") == "1" else 0
     flags |= AR_SEQUENTIAL_PREFILL if env("RQB200_SEQ_PREFILL", "0") == "1" else 0
     flags |= AR_BATCHED_DEEP_RING if env("RQB200_BATCHED_DEEP", "0") == "1" else 0
     flags |= AR_BATCHED_STREAMER if env("RQB200_BATCHED_STREAMER", "0") == "1" else 0
+    flags |= AR_ATTN_ONE_WARP if env("RQB200_ATTN_ONE_WARP", "0") == "1" else 0
     return {"flags": flags,
             "splits": [int(env("RQB200_SPLIT_" + k, "0")) for k in ("QKV", "PROJ", "FC1", "FC2")]}
 

@@ -226,6 +226,11 @@ int rqb200_dbg_conv_tc(const void* X16, const void* W16, const void* X16lo, cons
  * returns microseconds per stage.  workspace (device): >= 2*ctas*16 KB + 4 KB + 4*ctas bytes. */
 int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, int smem_bytes, int fan, int reps, void* workspace,
                      size_t workspace_bytes, float* us_per_stage);
+/* rqb200_dbg_chain2: the same PDL chain with the stage's two halves separable.  variant bit 0: every CTA reads `words` floats that
+ * another CTA of the previous kernel wrote (all of a thread's loads in flight); bit 1: every CTA writes `words` floats; bit 2: the
+ * reads go to lines nobody writes (clean) instead.  workspace (device) >= 3 * ctas * words * 4 bytes. */
+int rqb200_dbg_chain2(int variant, int words, int n_stages, int ctas, int threads, int smem_bytes, int reps, void* workspace,
+                      size_t workspace_bytes, float* us_per_stage);
 
 /* rqb200_dbg_rows_gemm: the large-M GEMM of the batched prefill / forward passes (csrc/conv_tc.cu launch_rows_gemm_tc: persistent
  * 128 x BN tiles, double-buffered TMEM): out[m,n] = act(sum_k X[m,k] W[n,k] + bias[n]) (+ residual[m,n]).  X [ceil(M/128)*128, K] and

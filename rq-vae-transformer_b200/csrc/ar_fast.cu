@@ -736,7 +736,7 @@ static int attn(const ArFast& f, FastWs& ws, const float* bqkv, h16* kc, h16* vc
                 cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
     if (f.attn4 && Tmax >= 16 && Tmax - 1 <= AF2_MAXROWS) {          // the body stack: four warps per (b, head)
-        const int rows = Tmax - 1;                                   // cached rows a step can read (row t is the new token)
+        const int rows = (Tmax - 1 + 7) & ~7;                        // cached rows a step can read (row t is the new token); 32 B-aligned float arrays behind them
         RQB_ENSURE_SMEM(attn2_smem(AF2_MAXROWS), attn_fast2_kernel);
         {   // 11 CTAs x 19.6 KB need the largest shared-memory carve-out (L1 is not used by this kernel)
             static std::atomic<uint64_t> carve{0};

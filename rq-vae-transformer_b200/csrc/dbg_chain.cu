@@ -99,6 +99,37 @@ __global__ void chain_persistent_kernel(float* a, float* b, int n_stages, int fa
     }
 }
 
+// chain2: what part of a dependent stage is the READ of freshly written data, what part the WRITE + completion flush?
+//   variant bit 0: every CTA reads `words` floats written by another CTA (all loads of a thread in flight, 16 x 16 B at a time)
+//   variant bit 1: every CTA writes `words` floats (after its loads have all returned: the stores carry their sum)
+//   variant bit 2: the reads go to a buffer nobody writes during the run (clean lines) instead of the previous stage's output
+__global__ void chain2_kernel(const float* __restrict__ in, float* __restrict__ out, int words, int variant) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int n4 = words >> 2;
+    const int src = (blockIdx.x * 7 + 1) % gridDim.x;
+    float4 acc = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (variant & 1) {
+        const float4* p = reinterpret_cast<const float4*>(in + (size_t)src * words);
+        for (int i0 = 0; i0 < n4; i0 += 16 * blockDim.x) {
+            float4 v[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int i = i0 + threadIdx.x + k * blockDim.x;
+                v[k] = i < n4 ? __ldcg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+        }
+    }
+    if (variant & 2) {
+        float4* q = reinterpret_cast<float4*>(out + (size_t)blockIdx.x * words);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcg(q + i, acc);
+    } else if (acc.x == -1.f) {
+        out[0] = acc.y;
+    }
+}
+
 }  // namespace rqb
 
 extern "C" int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, int smem_bytes, int fan, int reps, void* workspace,
@@ -171,6 +202,62 @@ extern "C" int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, i
         RQB_CUDA(cudaStreamSynchronize(st));
         RQB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(st);
+    if (us_per_stage) *us_per_stage = ms * 1000.f / ((float)n_stages * (float)reps);
+    return 0;
+}
+
+extern "C" int rqb200_dbg_chain2(int variant, int words, int n_stages, int ctas, int threads, int smem_bytes, int reps, void* workspace,
+                                 size_t workspace_bytes, float* us_per_stage) {
+    using namespace rqb;
+    if (variant < 0 || variant > 7 || words < 4 || (words & 3) || n_stages < 1 || ctas < 1 || threads < 32 || threads > 1024 || reps < 1)
+        return fail(RQB200_EINVAL, "dbg_chain2: bad arguments");
+    const size_t buf = (size_t)ctas * words * sizeof(float);
+    if (workspace_bytes < 3 * buf) return fail(RQB200_EINVAL, "dbg_chain2: workspace too small");
+    float* a = reinterpret_cast<float*>(workspace);
+    float* b = a + (size_t)ctas * words;
+    float* c = b + (size_t)ctas * words;
+    cudaStream_t st;
+    RQB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    RQB_CUDA(cudaMemsetAsync(workspace, 0, 3 * buf, st));
+    if (smem_bytes > 48 * 1024) RQB_CUDA(cudaFuncSetAttribute(chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    RQB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int s = 0; s < n_stages; s++) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)ctas);
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = (size_t)smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const float* in = (variant & 4) ? c : ((s & 1) ? b : a);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, chain2_kernel, in, (s & 1) ? a : b, words, variant);
+        if (e != cudaSuccess) {
+            cudaStreamEndCapture(st, &g);
+            return fail(RQB200_ECUDA, std::string("dbg_chain2 launch: ") + cudaGetErrorString(e));
+        }
+    }
+    RQB_CUDA(cudaStreamEndCapture(st, &g));
+    RQB_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    RQB_CUDA(cudaGraphLaunch(ge, st));
+    cudaEvent_t e0, e1;
+    RQB_CUDA(cudaEventCreate(&e0));
+    RQB_CUDA(cudaEventCreate(&e1));
+    RQB_CUDA(cudaEventRecord(e0, st));
+    for (int r = 0; r < reps; r++) RQB_CUDA(cudaGraphLaunch(ge, st));
+    RQB_CUDA(cudaEventRecord(e1, st));
+    RQB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    RQB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaGraphExecDestroy(ge);
+    cudaGraphDestroy(g);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaStreamDestroy(st);

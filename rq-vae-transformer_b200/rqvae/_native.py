@@ -113,6 +113,8 @@ def lib():
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.rqb200_dbg_chain.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_float)]
+    L.rqb200_dbg_chain2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                    C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -123,7 +125,7 @@ EXPORTS = ["rqb200_last_error", "rqb200_version", "rqb200_device_count", "rqb200
            "rqb200_ar_forward_workspace_bytes", "rqb200_ar_trace", "rqb200_ar_last_launches", "rqb200_vae_create",
            "rqb200_vae_destroy", "rqb200_vae_set_tensor", "rqb200_vae_finalize", "rqb200_vae_workspace_bytes",
            "rqb200_vae_decode", "rqb200_vae_decode_code", "rqb200_vae_encode", "rqb200_vae_last_launches",
-           "rqb200_dbg_gemm_tc", "rqb200_dbg_conv_tc", "rqb200_dbg_chain", "rqb200_dbg_rq_quantize",
+           "rqb200_dbg_gemm_tc", "rqb200_dbg_conv_tc", "rqb200_dbg_chain", "rqb200_dbg_chain2", "rqb200_dbg_rq_quantize",
            "rqb200_dbg_sample_logits", "rqb200_dbg_tma_rate", "rqb200_dbg_rows_gemm"]
 
 

@@ -103,6 +103,7 @@ __global__ void chain_persistent_kernel(float* a, float* b, int n_stages, int fa
 //   variant bit 0: every CTA reads `words` floats written by another CTA (all loads of a thread in flight, 16 x 16 B at a time)
 //   variant bit 1: every CTA writes `words` floats (after its loads have all returned: the stores carry their sum)
 //   variant bit 2: the reads go to a buffer nobody writes during the run (clean lines) instead of the previous stage's output
+//   variant bit 3: (with bit 1) the writes are scattered line by line over the whole buffer: a consumer's region has many writers
 __global__ void chain2_kernel(const float* __restrict__ in, float* __restrict__ out, int words, int variant) {
     tc::pdl_launch_dependents();
     tc::pdl_wait();
@@ -122,7 +123,14 @@ __global__ void chain2_kernel(const float* __restrict__ in, float* __restrict__ 
             for (int k = 0; k < 16; k++) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
         }
     }
-    if (variant & 2) {
+    if ((variant & 10) == 10) {
+        // bit 3: scattered writes -- 128 B line l of this CTA goes to line (l * ctas + cta): every 16 KB region a consumer reads was
+        // written by many different CTAs (the split-K partial planes / activation rows of the real chain)
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const size_t line = (size_t)(i >> 3) * gridDim.x + blockIdx.x;
+            __stcg(reinterpret_cast<float4*>(out) + line * 8 + (i & 7), acc);
+        }
+    } else if (variant & 2) {
         float4* q = reinterpret_cast<float4*>(out + (size_t)blockIdx.x * words);
         for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcg(q + i, acc);
     } else if (acc.x == -1.f) {
@@ -212,7 +220,7 @@ extern "C" int rqb200_dbg_chain(int mode, int n_stages, int ctas, int threads, i
 extern "C" int rqb200_dbg_chain2(int variant, int words, int n_stages, int ctas, int threads, int smem_bytes, int reps, void* workspace,
                                  size_t workspace_bytes, float* us_per_stage) {
     using namespace rqb;
-    if (variant < 0 || variant > 7 || words < 4 || (words & 3) || n_stages < 1 || ctas < 1 || threads < 32 || threads > 1024 || reps < 1)
+    if (variant < 0 || variant > 15 || words < 4 || (words & 3) || n_stages < 1 || ctas < 1 || threads < 32 || threads > 1024 || reps < 1)
         return fail(RQB200_EINVAL, "dbg_chain2: bad arguments");
     const size_t buf = (size_t)ctas * words * sizeof(float);
     if (workspace_bytes < 3 * buf) return fail(RQB200_EINVAL, "dbg_chain2: workspace too small");

@@ -210,18 +210,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ---- MMA issuer
+        // one polling lane: 31 idle lanes spinning on the same mbarrier only add shared-memory traffic next to the TMA writes
         const uint32_t idesc = tc::umma_idesc(128, BN, p.fmt);
-        if (tr && p.trace_w) {
-            // diagnostic: when did the weight tiles requested ahead of the dependency land?  (replaces the entry stamp)
-            for (int i = 0; i < (nkb < STAGES ? nkb : STAGES); i++) tc::mbar_wait(&full[i], 0);
-            if (lane == 0) p.trace[0] = tc::gtimer();
-        }
-        for (int i = 0; i < nkb; i++) {
-            const int s = i % STAGES;
-            tc::mbar_wait(&full[s], (i / STAGES) & 1);
-            tc::mbar_wait(&xfull[s], (i / STAGES) & 1);
-            tc::tc_fence_after();
-            if (lane == 0) {
+        if (lane == 0) {
+            if (tr && p.trace_w) {
+                // diagnostic: when did the weight tiles requested ahead of the dependency land?  (replaces the entry stamp)
+                for (int i = 0; i < (nkb < STAGES ? nkb : STAGES); i++) tc::mbar_wait(&full[i], 0);
+                p.trace[0] = tc::gtimer();
+            }
+            for (int i = 0; i < nkb; i++) {
+                const int s = i % STAGES;
+                tc::mbar_wait(&full[s], (i / STAGES) & 1);
+                tc::mbar_wait(&xfull[s], (i / STAGES) & 1);
+                tc::tc_fence_after();
                 const uint32_t a = tc::smem_u32(smem + s * STAGE_BYTES), b = a + GT_A_BYTES;
 #pragma unroll
                 for (int j = 0; j < 4; j++)
@@ -230,14 +231,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 tc::umma_commit(&empty[s]);                    // frees the ring slot once these MMAs have read it
                 if (i == nkb - 1) tc::umma_commit(tmem_full);  // accumulator complete
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4, thread <-> one output feature n, all batch columns
         tc::pdl_wait();
         const int q = warp & 3;
         const int n = tile * 128 + q * 32 + lane;
-        tc::mbar_wait(tmem_full, 0);
+        if (lane == 0) tc::mbar_wait(tmem_full, 0);              // (one polling lane per warp)
+        __syncwarp();
         tc::tc_fence_after();
         if (tr && warp == 2 && lane == 0) p.trace[2] = tc::gtimer();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);

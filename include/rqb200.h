@@ -89,11 +89,6 @@ typedef struct rqb200_block_weights {
     const void *wqkv, *wproj, *w1, *w2;            /* [3E,E] (rows: query|key|value), [E,E], [4E,E], [E,4E]; weight dtype */
     const float *bqkv, *bproj, *b1, *b2;           /* f32 biases */
     const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;    /* f32 */
-    /* fast tier, LayerNorm folded into the consuming Linear (both NULL: unfolded).  When set, the caller has prepared
-     *   wqkv = Wqkv diag(ln1_w),  bqkv = bqkv + Wqkv ln1_b,  cqkv[n] = sum_k wqkv[n,k]  (of the 16-bit-rounded values), [3E]
-     *   w1   = W1   diag(ln2_w),  b1   = b1   + W1   ln2_b,  c1[n]   = sum_k w1[n,k],                                   [4E]
-     * and LN(x) W^T + b is evaluated as rstd * (x W'^T - mean * c) + b' (csrc/ar_fast.cu). */
-    const float *cqkv, *c1;
 } rqb200_block_weights;
 
 typedef struct rqb200_ar_config {

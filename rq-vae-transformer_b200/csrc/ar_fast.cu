@@ -87,10 +87,7 @@ ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ parti
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e4 < E4) {
             float4 pr[12];
-            if (xn) {                        // (g == NULL: plain normalisation -- gamma / beta folded into the consuming weights)
-                gg[k] = g ? reinterpret_cast<const float4*>(g)[e4] : make_float4(1.f, 1.f, 1.f, 1.f);
-                bb[k] = g ? reinterpret_cast<const float4*>(be)[e4] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            if (xn) { gg[k] = reinterpret_cast<const float4*>(g)[e4]; bb[k] = reinterpret_cast<const float4*>(be)[e4]; }
 #pragma unroll
             for (int i = 0; i < 12; i++)
                 if (i < S12) pr[i] = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
@@ -133,74 +130,6 @@ ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ parti
     } else {
         TR_OUT(tr);
     }
-}
-
-// ---- LayerNorm folded into the consuming Linear (fast tier default; reference arithmetic: attentions.py:117-122 LN -> Linear).
-// LN(x) W^T + b  =  rstd * (x W'^T - mean * c) + d   with  W' = W diag(gamma),  c[n] = sum_k W'[n,k],  d = b + W beta
-// (W', c, d are prepared by the host when the engine is created).  The GEMM then consumes the RAW residual row in 16-bit, and the
-// row statistics are only needed by the kernel that reduces the GEMM's split-K partials two stages later.  That takes the row-wide
-// reduction out of the stage between two GEMMs: ln_reduce_kernel needs one CTA per row (64 CTAs pulling 74 KB each, 3.0-3.5 us
-// from dependency to statistics in the stage trace); xreduce_kernel is elementwise, one warp per 128-element row chunk on a
-// 148-CTA grid, and emits per-chunk (sum, M2) pairs that the consumer merges (Chan's formula: no E[x^2] - mean^2 cancellation).
-// Same summation order as ln_reduce_kernel -> the fp32 residual stream is bit-identical between the two forms.
-__global__ void __launch_bounds__(256)
-xreduce_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int S, const float* __restrict__ bias,
-               const float* __restrict__ extra, float* __restrict__ x_out, h16* __restrict__ x16, float2* __restrict__ stats, int B, int E,
-               int bf, long long* tr) {
-    tc::pdl_launch_dependents();
-    TR_IN(tr);
-    tc::pdl_wait();
-    TR_DEP(tr);
-    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-    const int nchunk = E >> 7;
-    const int total = B * nchunk;
-    const int S12 = S < 12 ? S : 12;
-    for (int gidx = blockIdx.x * wpc + (threadIdx.x >> 5); gidx < total; gidx += gridDim.x * wpc) {
-        const int b = gidx / nchunk, ch = gidx - b * nchunk;
-        const int e4 = ch * 32 + lane;
-        float4 pr[12];
-#pragma unroll
-        for (int i = 0; i < 12; i++)
-            if (i < S12) pr[i] = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x_in) v = reinterpret_cast<const float4*>(x_in + (int64_t)b * E)[e4];
-        if (bias) { const float4 t = reinterpret_cast<const float4*>(bias)[e4]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-#pragma unroll
-        for (int i = 0; i < 12; i++)
-            if (i < S12) { v.x += pr[i].x; v.y += pr[i].y; v.z += pr[i].z; v.w += pr[i].w; }
-        for (int i = 12; i < S; i++) {
-            const float4 p0 = reinterpret_cast<const float4*>(partial + ((int64_t)i * B + b) * E)[e4];
-            v.x += p0.x; v.y += p0.y; v.z += p0.z; v.w += p0.w;
-        }
-        if (extra) { const float4 t = reinterpret_cast<const float4*>(extra)[e4]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-        if (x_out) reinterpret_cast<float4*>(x_out + (int64_t)b * E)[e4] = v;
-        if (x16) {
-            uint2 pk;
-            pk.x = pack_h16x2(v.x, v.y, bf);
-            pk.y = pack_h16x2(v.z, v.w, bf);
-            reinterpret_cast<uint2*>(x16 + (int64_t)b * E)[e4] = pk;
-        }
-        if (stats) {
-            const float sum = warp_sum((v.x + v.y) + (v.z + v.w));
-            const float cm = sum * (1.0f / 128.0f);
-            const float d0 = v.x - cm, d1 = v.y - cm, d2 = v.z - cm, d3 = v.w - cm;
-            const float m2 = warp_sum(fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3))));
-            if (lane == 0) stats[gidx] = make_float2(sum, m2);
-        }
-    }
-    TR_OUT(tr);
-}
-
-// warp-collective: (mean, rstd) of row b from its per-chunk (sum, M2) pairs; nchunk = E / 128 <= 36
-__device__ __forceinline__ float2 row_stats(const float2* __restrict__ st, int nchunk, int E, int lane) {
-    float2 a = lane < nchunk ? st[lane] : make_float2(0.f, 0.f);
-    float2 b2 = lane + 32 < nchunk ? st[lane + 32] : make_float2(0.f, 0.f);
-    const float mean = warp_sum(a.x + b2.x) / (float)E;
-    float t = 0.f;
-    if (lane < nchunk) { const float d = a.x * (1.0f / 128.0f) - mean; t = fmaf(128.0f * d, d, a.y); }
-    if (lane + 32 < nchunk) { const float d = b2.x * (1.0f / 128.0f) - mean; t += fmaf(128.0f * d, d, b2.y); }
-    const float var = warp_sum(t) / (float)E;
-    return make_float2(mean, rsqrtf(var + 1e-5f));
 }
 
 // The batched passes' LayerNorm (prefill / teacher-forced forward: thousands of rows, no split-K partials): one WARP per row, the
@@ -246,8 +175,7 @@ ln_rows_kernel(const float* __restrict__ x_in, const float* __restrict__ extra, 
             for (int k = 0; k < NV; k++) {
                 const int e4 = lane + 32 * k;
                 if (e4 < E4) {
-                    float4 gg = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);     // (folded form: gamma / beta live in the weights)
-                    if (g) { gg = reinterpret_cast<const float4*>(g)[e4]; bb = reinterpret_cast<const float4*>(be)[e4]; }
+                    const float4 gg = reinterpret_cast<const float4*>(g)[e4], bb = reinterpret_cast<const float4*>(be)[e4];
                     uint2 pk;
                     pk.x = pack_h16x2((v[k].x - mean) * rstd * gg.x + bb.x, (v[k].y - mean) * rstd * gg.y + bb.y, bf);
                     pk.y = pack_h16x2((v[k].z - mean) * rstd * gg.z + bb.z, (v[k].w - mean) * rstd * gg.w + bb.w, bf);
@@ -260,14 +188,13 @@ ln_rows_kernel(const float* __restrict__ x_in, const float* __restrict__ extra, 
 
 // h = 16-bit(gelu(sum_s partial[s] + bias))   (only when fc1 runs split-K); 4 elements per thread, all partial loads in flight
 __global__ void __launch_bounds__(256)
-act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, const float* __restrict__ cvec,
-                  const float2* __restrict__ stats, int E, h16* __restrict__ h, int B, int N, int bf, long long* tr) {
+act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, h16* __restrict__ h, int B, int N, int bf,
+                  long long* tr) {
     tc::pdl_launch_dependents();
     TR_IN(tr);
     tc::pdl_wait();
     TR_DEP(tr);
     const int64_t total4 = (int64_t)B * N / 4;
-    // (total4 is a multiple of 32 and a warp's 32 float4 lie in one row: N % 128 == 0)
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256) {
         const int n = (int)((i * 4) % N);
         float4 pr[4];
@@ -275,31 +202,12 @@ act_reduce_kernel(const float* __restrict__ partial, int S, const float* __restr
         for (int s = 0; s < 4; s++)
             if (s < S) pr[s] = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)s * B * N) + i);
         float4 v = *reinterpret_cast<const float4*>(bias + n);
-        if (cvec == nullptr) {
 #pragma unroll
-            for (int s = 0; s < 4; s++)
-                if (s < S) { v.x += pr[s].x; v.y += pr[s].y; v.z += pr[s].z; v.w += pr[s].w; }
-            for (int s = 4; s < S; s++) {
-                float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)s * B * N) + i);
-                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-            }
-        } else {
-            // folded LayerNorm: h = gelu(d + rstd * (sum_s partial - mean * c))
-            const int b = (int)((i * 4) / N);
-            const float2 ms = row_stats(stats + (int64_t)b * (E >> 7), E >> 7, E, threadIdx.x & 31);
-            const float4 c4 = *reinterpret_cast<const float4*>(cvec + n);
-            float4 a = pr[0];
-#pragma unroll
-            for (int s = 1; s < 4; s++)
-                if (s < S) { a.x += pr[s].x; a.y += pr[s].y; a.z += pr[s].z; a.w += pr[s].w; }
-            for (int s = 4; s < S; s++) {
-                float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)s * B * N) + i);
-                a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
-            }
-            v.x = fmaf(ms.y, fmaf(-ms.x, c4.x, a.x), v.x);
-            v.y = fmaf(ms.y, fmaf(-ms.x, c4.y, a.y), v.y);
-            v.z = fmaf(ms.y, fmaf(-ms.x, c4.z, a.z), v.z);
-            v.w = fmaf(ms.y, fmaf(-ms.x, c4.w, a.w), v.w);
+        for (int s = 0; s < 4; s++)
+            if (s < S) { v.x += pr[s].x; v.y += pr[s].y; v.z += pr[s].z; v.w += pr[s].w; }
+        for (int s = 4; s < S; s++) {
+            float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)s * B * N) + i);
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
         }
         float r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -339,9 +247,9 @@ __device__ __forceinline__ float af_transpose_reduce(float (&pv)[32], int lane) 
 }
 
 __global__ void __launch_bounds__(128)
-attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, const float* __restrict__ cvec,
-                 const float2* __restrict__ stats, h16* __restrict__ kc, h16* __restrict__ vc, h16* __restrict__ att, int B, int E, int nh,
-                 int Tmax, const int* __restrict__ t_ptr, int t_host, int bf, long long* tr) {
+attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, h16* __restrict__ kc, h16* __restrict__ vc,
+                 h16* __restrict__ att, int B, int E, int nh, int Tmax, const int* __restrict__ t_ptr, int t_host, int bf,
+                 long long* tr) {
     extern __shared__ float af_smem[];              // ps[4][tp]
     const int tp = (Tmax + 31) & ~31;
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
@@ -357,10 +265,9 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
     h16* kb = kc + ((int64_t)(b * nh + h) * Tmax) * 64;
     h16* vb = vc + ((int64_t)(b * nh + h) * Tmax) * 64;
     const int c = h * 64 + 2 * lane;
-    const bool fold = cvec != nullptr;
-    float2 q = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[c], bqkv[c + 1]);
-    float2 k = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[E + c], bqkv[E + c + 1]);
-    float2 v = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[2 * E + c], bqkv[2 * E + c + 1]);
+    float2 q = make_float2(bqkv[c], bqkv[c + 1]);
+    float2 k = make_float2(bqkv[E + c], bqkv[E + c + 1]);
+    float2 v = make_float2(bqkv[2 * E + c], bqkv[2 * E + c + 1]);
 #pragma unroll 4
     for (int s = 0; s < S; s++) {
         const float* p = part + ((int64_t)s * B + b) * 3 * E;
@@ -368,12 +275,6 @@ attn_fast_kernel(const float* __restrict__ part, int S, const float* __restrict_
         float2 bb = *reinterpret_cast<const float2*>(p + E + c);
         float2 cc = *reinterpret_cast<const float2*>(p + 2 * E + c);
         q.x += a.x; q.y += a.y; k.x += bb.x; k.y += bb.y; v.x += cc.x; v.y += cc.y;
-    }
-    if (fold) {      // folded LayerNorm: value = d + rstd * (sum_s partial - mean * c)
-        const float2 ms = row_stats(stats + (int64_t)b * (E >> 7), E >> 7, E, lane);
-        q.x = fmaf(ms.y, fmaf(-ms.x, cvec[c], q.x), bqkv[c]);                 q.y = fmaf(ms.y, fmaf(-ms.x, cvec[c + 1], q.y), bqkv[c + 1]);
-        k.x = fmaf(ms.y, fmaf(-ms.x, cvec[E + c], k.x), bqkv[E + c]);         k.y = fmaf(ms.y, fmaf(-ms.x, cvec[E + c + 1], k.y), bqkv[E + c + 1]);
-        v.x = fmaf(ms.y, fmaf(-ms.x, cvec[2 * E + c], v.x), bqkv[2 * E + c]); v.y = fmaf(ms.y, fmaf(-ms.x, cvec[2 * E + c + 1], v.y), bqkv[2 * E + c + 1]);
     }
     const uint32_t k2 = pack_h16x2(k.x, k.y, bf), v2 = pack_h16x2(v.x, v.y, bf);
     *reinterpret_cast<uint32_t*>(kb + (int64_t)t * 64 + 2 * lane) = k2;
@@ -456,9 +357,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __global__ void __launch_bounds__(128, 11)
-attn_fast2_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, const float* __restrict__ cvec,
-                  const float2* __restrict__ stats, h16* __restrict__ kc, h16* __restrict__ vc, h16* __restrict__ att, int B, int E, int nh,
-                  int Tmax, int rows, const int* __restrict__ t_ptr, int t_host, int bf, long long* tr) {
+attn_fast2_kernel(const float* __restrict__ part, int S, const float* __restrict__ bqkv, h16* __restrict__ kc, h16* __restrict__ vc,
+                  h16* __restrict__ att, int B, int E, int nh, int Tmax, int rows, const int* __restrict__ t_ptr, int t_host, int bf,
+                  long long* tr) {
     extern __shared__ __align__(128) uint8_t af2_smem[];
     uint8_t* Ks = af2_smem;                                   // [rows][128 B], chunk c of row j at ((c ^ (j & 7)) << 4)
     uint8_t* Vs = Ks + (size_t)rows * 128;
@@ -490,17 +391,11 @@ attn_fast2_kernel(const float* __restrict__ part, int S, const float* __restrict
     // ---- q / k / v of the new token: warp 0 -> q, warp 1 -> k, warp 2 -> v (value = bias + p0 + p1 + ..., split order)
     if (w < 3) {
         const int c = h * 64 + 2 * lane;
-        const bool fold = cvec != nullptr;
-        float2 a = fold ? make_float2(0.f, 0.f) : make_float2(bqkv[w * E + c], bqkv[w * E + c + 1]);
+        float2 a = make_float2(bqkv[w * E + c], bqkv[w * E + c + 1]);
 #pragma unroll 4
         for (int s = 0; s < S; s++) {
             const float2 pp = *reinterpret_cast<const float2*>(part + ((int64_t)s * B + b) * 3 * E + w * E + c);
             a.x += pp.x; a.y += pp.y;
-        }
-        if (fold) {      // folded LayerNorm: value = d + rstd * (sum_s partial - mean * c)
-            const float2 ms = row_stats(stats + (int64_t)b * (E >> 7), E >> 7, E, lane);
-            a.x = fmaf(ms.y, fmaf(-ms.x, cvec[w * E + c], a.x), bqkv[w * E + c]);
-            a.y = fmaf(ms.y, fmaf(-ms.x, cvec[w * E + c + 1], a.y), bqkv[w * E + c + 1]);
         }
         const uint32_t a2 = pack_h16x2(a.x, a.y, bf);
         const float2 af = unpack_h16x2(a2, bf);
@@ -732,8 +627,6 @@ struct ArFast {
     bool use_graph = true, use_pdl = true, attn4 = true, deep = true, l2pf = false, batched_prefill = true, batched_deep = false, batched_streamer = false;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
     int n_sm = 148;
-    size_t pad_smem = 0, pad_smem_act = 0;   // dynamic shared memory requested (not used) by the small kernels: spreads their CTAs
-    bool fold = false;                   // LayerNorm folded into qkv / fc1 (rqb200_block_weights.cqkv / c1 given)
     // diagnostic stage trace (cfg.flags & RQB200_AR_TRACE)
     bool trace = false, trace_w = false;
     mutable long long* tr_base = nullptr;
@@ -749,7 +642,6 @@ struct FastWs {
     long long* trace;
     float *XB, *XH, *P, *LOGITS;
     h16 *XN, *ATT, *Hh, *S;
-    float2 *ST1, *ST2;           // folded LayerNorm: per-row-chunk (sum, M2) of LN1's / LN2's input rows
     h16 *kc_body, *vc_body, *kc_head, *vc_head;
     // batched prefill (M = B * T rows, token-major)
     int64_t Mmax;
@@ -789,8 +681,6 @@ static size_t fast_layout(const ArFast& f, int B, void* base, size_t cap, FastWs
     w.ATT = a.take<h16>(B * E);
     w.Hh = a.take<h16>(B * 4 * E);
     w.S = a.take<h16>((int64_t)B * c.code_dim);
-    w.ST1 = a.take<float2>((int64_t)B * (E / 128));
-    w.ST2 = a.take<float2>((int64_t)B * (E / 128));
     const int64_t per_body = (int64_t)B * c.n_head * Tb * 64, per_head = (int64_t)B * c.n_head * c.D * 64;
     w.kc_body = a.take<h16>(per_body * c.n_body);
     w.vc_body = a.take<h16>(per_body * c.n_body);
@@ -839,25 +729,12 @@ static int ln(const ArFast& f, const char* name, int rows, const float* x_in, co
         return RQB_LN_ROWS(36);
 #undef RQB_LN_ROWS
     }
-    // (pad_smem: never-touched dynamic shared memory -- it only keeps the block scheduler from stacking several of these CTAs on one SM
-    //  next to a resident GEMM CTA, which would leave most SMs -- and their L2 bandwidth -- idle during the stage)
-    return launch_pdl(ln_reduce_kernel<384, 3>, dim3((unsigned)rows), dim3(384), f.pad_smem, st, f.use_pdl, x_in, partial, S, bias, extra,
-                      x_out, g, be, xn, rows, E, f.bf, tr_slot(f, name));
+    return launch_pdl(ln_reduce_kernel<384, 3>, dim3((unsigned)rows), dim3(384), (size_t)0, st, f.use_pdl, x_in, partial, S, bias, extra, x_out,
+                      g, be, xn, rows, E, f.bf, tr_slot(f, name));
 }
 
-// folded form of ln(): elementwise on a one-CTA-per-SM grid (every CTA works: grids of 64 / 128 fat CTAs hand over ~1 us slower
-// than 74 / 148, profiles/bench_chain3_r2.txt)
-static int xr(const ArFast& f, const char* name, int rows, const float* x_in, const float* partial, int S, const float* bias,
-              const float* extra, float* x_out, h16* x16, float2* stats, cudaStream_t st) {
-    const int E = f.cfg.embed_dim;
-    const int total = rows * (E / 128);
-    const int wpc = std::max(1, std::min(8, (int)ceil_div(total, f.n_sm)));
-    return launch_pdl(xreduce_kernel, dim3((unsigned)f.n_sm), dim3((unsigned)(32 * wpc)), f.pad_smem, st, f.use_pdl, x_in, partial, S, bias,
-                      extra, x_out, x16, stats, rows, E, f.bf, tr_slot(f, name));
-}
-
-static int attn(const ArFast& f, FastWs& ws, const float* bqkv, const float* cvec, h16* kc, h16* vc, int Tmax, const int* t_ptr,
-                int t_host, cudaStream_t st) {
+static int attn(const ArFast& f, FastWs& ws, const float* bqkv, h16* kc, h16* vc, int Tmax, const int* t_ptr, int t_host,
+                cudaStream_t st) {
     const rqb200_ar_config& c = f.cfg;
     if (f.attn4 && Tmax >= 16 && Tmax - 1 <= AF2_MAXROWS) {          // the body stack: four warps per (b, head)
         const int rows = (Tmax - 1 + 7) & ~7;                        // cached rows a step can read (row t is the new token); 32 B-aligned float arrays behind them
@@ -872,13 +749,13 @@ static int attn(const ArFast& f, FastWs& ws, const float* bqkv, const float* cve
             }
         }
         return launch_pdl(attn_fast2_kernel, dim3((unsigned)(f.B * c.n_head)), dim3(128), attn2_smem(rows), st, f.use_pdl,
-                          (const float*)ws.P, f.split_qkv, bqkv, cvec, (const float2*)ws.ST1, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax,
-                          rows, t_ptr, t_host, f.bf, tr_slot(f, "attn"));
+                          (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, rows, t_ptr, t_host,
+                          f.bf, tr_slot(f, "attn"));
     }
     const size_t smem = (size_t)(4 * ((Tmax + 31) & ~31)) * sizeof(float);
     return launch_pdl(attn_fast_kernel, dim3((unsigned)ceil_div(f.B * c.n_head, 4)), dim3(128), smem, st, f.use_pdl,
-                      (const float*)ws.P, f.split_qkv, bqkv, cvec, (const float2*)ws.ST1, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax,
-                      t_ptr, t_host, f.bf, tr_slot(f, "attn"));
+                      (const float*)ws.P, f.split_qkv, bqkv, kc, vc, ws.ATT, f.B, c.embed_dim, c.n_head, Tmax, t_ptr, t_host, f.bf,
+                      tr_slot(f, "attn"));
 }
 
 // one transformer stack on the single new token of every batch row; x lives in `x` (fp32); residual additions are deferred
@@ -892,47 +769,33 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
     const int E = c.embed_dim, B = f.B;
     const int64_t per = (int64_t)B * c.n_head * Tmax * 64;
     const float* nof = nullptr;
-    const bool fold = f.fold;
     for (size_t l = 0; l < blocks.size(); l++) {
         const rqb200_block_weights& bw = blocks[l];
         const bool first = l == 0;
         // LN1 (+ pending fc2 reduction of the previous block)
         const bool pend = l > 0;
-        if (fold) {
-            RQB_TRY(xr(f, "ln1", B, first ? x_src : x, pend ? ws.P : nof, pend ? f.split_fc2 : 0, pend ? blocks[l - 1].b2 : nof,
-                       first ? pending_extra : nof, x, ws.XN, ws.ST1, st));
-        } else {
-            RQB_TRY(ln(f, "ln1", B, first ? x_src : x, pend ? ws.P : nof, pend ? f.split_fc2 : 0, pend ? blocks[l - 1].b2 : nof,
-                       first ? pending_extra : nof, x, bw.ln1_w, bw.ln1_b, ws.XN, st));
-        }
+        RQB_TRY(ln(f, "ln1", B, first ? x_src : x, pend ? ws.P : nof, pend ? f.split_fc2 : 0, pend ? blocks[l - 1].b2 : nof,
+                   first ? pending_extra : nof, x, bw.ln1_w, bw.ln1_b, ws.XN, st));
         RQB_TRY(gemm(f, "qkv", maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr, 0,
                      st));
-        RQB_TRY(attn(f, ws, bw.bqkv, fold ? bw.cqkv : nof, kc + per * l, vc + per * l, Tmax, t_ptr, t_host, st));
+        RQB_TRY(attn(f, ws, bw.bqkv, kc + per * l, vc + per * l, Tmax, t_ptr, t_host, st));
         RQB_TRY(gemm(f, "proj", maps[l].proj, f.tx_att, E, E, B, f.split_proj, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr,
                      0, st));
-        if (fold) {
-            RQB_TRY(xr(f, "ln2", B, x, ws.P, f.split_proj, bw.bproj, nof, x, ws.XN, ws.ST2, st));
-        } else {
-            RQB_TRY(ln(f, "ln2", B, x, ws.P, f.split_proj, bw.bproj, nof, x, bw.ln2_w, bw.ln2_b, ws.XN, st));
-        }
-        if (f.split_fc1 == 1 && !fold) {
+        RQB_TRY(ln(f, "ln2", B, x, ws.P, f.split_proj, bw.bproj, nof, x, bw.ln2_w, bw.ln2_b, ws.XN, st));
+        if (f.split_fc1 == 1) {
             RQB_TRY(gemm(f, "fc1", maps[l].fc1, f.tx_xn, 4 * E, E, B, 1, GT_H16_GELU, bw.b1, 1.f, ws.Hh, nullptr, nullptr, 0, nullptr, 0, st));
         } else {
             RQB_TRY(gemm(f, "fc1", maps[l].fc1, f.tx_xn, 4 * E, E, B, f.split_fc1, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0,
                          nullptr, 0, st));
             RQB_TRY(launch_pdl(act_reduce_kernel, dim3((unsigned)std::min<int64_t>(ceil_div((int64_t)B * 4 * E / 4, 256), 1184)), dim3(256),
-                               f.pad_smem_act, st, f.use_pdl, (const float*)ws.P, f.split_fc1, bw.b1, fold ? bw.c1 : nof, (const float2*)ws.ST2, E,
-                               ws.Hh, B, 4 * E, f.bf, tr_slot(f, "act_reduce")));
+                               (size_t)0, st, f.use_pdl, (const float*)ws.P, f.split_fc1, bw.b1, ws.Hh, B, 4 * E, f.bf,
+                               tr_slot(f, "act_reduce")));
         }
         RQB_TRY(gemm(f, "fc2", maps[l].fc2, f.tx_h, E, 4 * E, B, f.split_fc2, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr, 0,
                      st));
     }
     // fold the last block's pending fc2 reduction into x (x is final on return) -- and the caller's LayerNorm, if any
-    if (fold && !fin_g) {
-        RQB_TRY(xr(f, "finalize", B, x, ws.P, f.split_fc2, blocks.back().b2, nof, x, nullptr, nullptr, st));
-    } else {
-        RQB_TRY(ln(f, "finalize", B, x, ws.P, f.split_fc2, blocks.back().b2, nof, x, fin_g, fin_b, fin_g ? ws.XN : nullptr, st));
-    }
+    RQB_TRY(ln(f, "finalize", B, x, ws.P, f.split_fc2, blocks.back().b2, nof, x, fin_g, fin_b, fin_g ? ws.XN : nullptr, st));
     return 0;
 }
 
@@ -1028,7 +891,6 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     ArFast* f = new ArFast();
     f->cfg = cfg; f->w = w; f->body = body; f->head = head;
     f->bf = cfg.weight_dtype == RQB200_BF16 ? 1 : 0;
-    f->fold = !body.empty() && body[0].cqkv != nullptr;
     f->use_graph = !(cfg.flags & RQB200_AR_NO_GRAPH);
     f->use_pdl = !(cfg.flags & RQB200_AR_NO_PDL);
     f->trace = (cfg.flags & RQB200_AR_TRACE) != 0;
@@ -1036,8 +898,6 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     f->l2pf = (cfg.flags & RQB200_AR_L2_PREFETCH) != 0;
     f->deep = !(cfg.flags & RQB200_AR_SHALLOW_RING);
     f->attn4 = !(cfg.flags & RQB200_AR_ATTN_ONE_WARP);
-    f->pad_smem = (size_t)((cfg.flags >> 16) & 0xff) << 10;          // (experiment knobs: KB in bits 16..23 / 24..31)
-    f->pad_smem_act = (size_t)((cfg.flags >> 24) & 0x7f) << 10;
     f->batched_prefill = !(cfg.flags & RQB200_AR_SEQUENTIAL_PREFILL);
     f->batched_deep = (cfg.flags & RQB200_AR_BATCHED_DEEP_RING) != 0;
     f->batched_streamer = (cfg.flags & RQB200_AR_BATCHED_STREAMER) != 0;
@@ -1110,7 +970,7 @@ static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blo
     const bool rows = M > 256 && !f.batched_streamer;
     for (size_t l = 0; l < blocks.size(); l++) {
         const rqb200_block_weights& bw = blocks[l];
-        RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, f.fold ? nof : bw.ln1_w, f.fold ? nof : bw.ln1_b, bb.XN, st));
+        RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, bw.ln1_w, bw.ln1_b, bb.XN, st));
         if (rows) {
             RQB_TRY(launch_rows_gemm_tc(bb.XN, bw.wqkv, bw.bqkv, nullptr, nullptr, bb.QKV, 0, f.bf, M, 3 * E, E, st));
         } else {
@@ -1128,7 +988,7 @@ static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blo
             p.bias = bw.bproj; p.out = bb.X; p.residual = bb.X; p.ld_res = E;
             RQB_TRY(launch_gemm_tc(maps[l].proj, tx_att, p, pdl, st));
         }
-        RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, f.fold ? nof : bw.ln2_w, f.fold ? nof : bw.ln2_b, bb.XN, st));
+        RQB_TRY(ln(f, "", (int)M, bb.X, nof, 0, nof, nof, nullptr, bw.ln2_w, bw.ln2_b, bb.XN, st));
         if (rows) {
             RQB_TRY(launch_rows_gemm_tc(bb.XN, bw.w1, bw.b1, nullptr, nullptr, bb.H, 1, f.bf, M, 4 * E, E, st));
             RQB_TRY(launch_rows_gemm_tc(bb.H, bw.w2, bw.b2, bb.X, bb.X, nullptr, 0, f.bf, M, E, 4 * E, st));

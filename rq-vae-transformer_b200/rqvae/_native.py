@@ -19,7 +19,7 @@ c_f32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("wqkv", "wproj", "w1", "w2", "bqkv", "bproj", "b1", "b2",
-                                          "ln1_w", "ln1_b", "ln2_w", "ln2_b", "cqkv", "c1")]
+                                          "ln1_w", "ln1_b", "ln2_w", "ln2_b")]
 
 
 class ArConfig(C.Structure):
@@ -178,9 +178,7 @@ def ar_engine_options():
     flags |= AR_BATCHED_DEEP_RING if env("RQB200_BATCHED_DEEP", "0") == "1" else 0
     flags |= AR_BATCHED_STREAMER if env("RQB200_BATCHED_STREAMER", "0") == "1" else 0
     flags |= AR_ATTN_ONE_WARP if env("RQB200_ATTN_ONE_WARP", "0") == "1" else 0
-    flags |= (int(env("RQB200_PAD_SMEM_KB", "0")) & 0xff) << 16
-    flags |= (int(env("RQB200_PAD_SMEM_ACT_KB", "0")) & 0x7f) << 24
-    return {"flags": flags, "ln_fold": env("RQB200_LN_FOLD", "1") != "0",
+    return {"flags": flags,
             "splits": [int(env("RQB200_SPLIT_" + k, "0")) for k in ("QKV", "PROJ", "FC1", "FC2")]}
 
 

@@ -55,18 +55,6 @@ class _Stack(_Holder):
         self.blocks = nn.ModuleList([_Block(cfg.block) for _ in range(cfg.n_layer)])
 
 
-def fold_layernorm_into_linear(weight, bias, ln_weight, ln_bias, dtype):
-    """LayerNorm folded into the Linear that consumes it (fast tier; reference arithmetic attentions.py:117-122):
-        LN(x) W^T + b  =  rstd * (x W'^T - mean * c) + d,   W' = W diag(gamma) rounded to `dtype`,
-        c[n] = sum_k W'[n,k] (of the ROUNDED values, what the tensor cores multiply),   d = b + W beta.
-    Returns (W' [out,in] dtype, d [out] f32, c [out] f32)."""
-    w32 = weight.detach().float()
-    wf = (w32 * ln_weight.detach().float()[None, :]).to(dtype).contiguous()
-    cvec = wf.float().sum(1)
-    dvec = bias.detach().float() + w32 @ ln_bias.detach().float()
-    return wf, dvec, cvec
-
-
 class RQTransformer(Stage2Model):
     def __init__(self, config):
         super().__init__()
@@ -176,33 +164,18 @@ class RQTransformer(Stage2Model):
             keep.append(t)
             return t.data_ptr()
 
-        fold = mode == N.MODE_FAST and opts.get("ln_fold", False)
-
-        def folded(weight, bias, ln):
-            wf, dvec, cvec = fold_layernorm_into_linear(weight, bias, ln.weight, ln.bias, wdt)
-            keep.append(wf)
-            return wf.data_ptr(), f32(dvec), f32(cvec)
-
         def blocks(stack):
             arr = (N.BlockWeights * len(stack.blocks))()
             for i, b in enumerate(stack.blocks):
                 a = b.attn
                 wqkv = torch.cat([a.query.weight, a.key.weight, a.value.weight], 0)
                 bqkv = torch.cat([a.query.bias, a.key.bias, a.value.bias], 0)
-                if fold:
-                    arr[i].wqkv, arr[i].bqkv, arr[i].cqkv = folded(wqkv, bqkv, b.ln1)
-                    arr[i].w1, arr[i].b1, arr[i].c1 = folded(b.mlp[0].weight, b.mlp[0].bias, b.ln2)
-                else:
-                    arr[i].wqkv, arr[i].bqkv = wt(wqkv), f32(bqkv)
-                    arr[i].w1, arr[i].b1 = wt(b.mlp[0].weight), f32(b.mlp[0].bias)
+                arr[i].wqkv, arr[i].bqkv = wt(wqkv), f32(bqkv)
+                arr[i].w1, arr[i].b1 = wt(b.mlp[0].weight), f32(b.mlp[0].bias)
                 arr[i].wproj, arr[i].bproj = wt(a.proj.weight), f32(a.proj.bias)
                 arr[i].w2, arr[i].b2 = wt(b.mlp[2].weight), f32(b.mlp[2].bias)
                 arr[i].ln1_w, arr[i].ln1_b = f32(b.ln1.weight), f32(b.ln1.bias)
                 arr[i].ln2_w, arr[i].ln2_b = f32(b.ln2.weight), f32(b.ln2.bias)
-                if i > 0 and os.environ.get("RQB200_DBG_SHARED_PARAMS", "0") == "1":
-                    # TIMING EXPERIMENT ONLY (wrong results): every block reads block 0's small vectors, so they stay cache-resident
-                    for n_ in ("bqkv", "bproj", "b1", "b2", "ln1_w", "ln1_b", "ln2_w", "ln2_b", "cqkv", "c1"):
-                        setattr(arr[i], n_, getattr(arr[0], n_))
             return arr
 
         cfg = N.ArConfig()

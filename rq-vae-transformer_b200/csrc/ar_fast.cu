@@ -544,6 +544,118 @@ prefill_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ kc, h16* __re
     }
 }
 
+// The same causal attention for prefixes of at most 64 tokens (the 8x8 grids' body pass: T = cond_len + 63) on the warp-level tensor
+// cores: Q, K, V of one (group, head) are staged in shared memory (144 B rows: conflict-free ldmatrix), each of the four warps owns
+// 16 query rows -- S = Q K^T as 8 n-tiles x 4 k-steps of mma.sync.m16n8k16 (fp32 accumulate), scale, causal mask, row softmax in
+// registers (quad shuffles), the probabilities repacked as 16-bit A fragments (the m16n8 accumulator pair of two adjacent key tiles IS
+// the m16k16 A fragment), O = P V with V through ldmatrix.trans.  ~100 tensor instructions per warp instead of ~270 k scalar FMAs per
+// CTA.  (Not the tcgen05 path: 64 x 64 x 64 per head is two orders of magnitude below a UMMA tile's worth of work.)
+template <bool BF>
+__device__ __forceinline__ void pa_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if (BF)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void pa_ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void pa_ldsm4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+constexpr int PM_ROW = 144;                           // bytes per staged row (64 x 16-bit + 16 B pad)
+template <bool BF>
+__global__ void __launch_bounds__(128)
+prefill_attn_mma_kernel(const h16* __restrict__ qkv, h16* __restrict__ kc, h16* __restrict__ vc, h16* __restrict__ att, int G, int T, int E,
+                        int nh, int Tmax) {
+    __shared__ __align__(16) uint8_t sm[3 * 64 * PM_ROW];
+    uint8_t* Qs = sm;
+    uint8_t* Ks = sm + 64 * PM_ROW;
+    uint8_t* Vs = sm + 2 * 64 * PM_ROW;
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int g = blockIdx.x / nh, h = blockIdx.x % nh;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // ---- stage Q, K, V rows [0, T) (rows beyond T: zeros); K / V also go to the cache
+    for (int i = threadIdx.x; i < 3 * 64 * 8; i += 128) {
+        const int mat = i / 512, t = (i >> 3) & 63, c = i & 7;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (t < T) v = *reinterpret_cast<const uint4*>(qkv + ((int64_t)t * G + g) * 3 * E + mat * E + h * 64 + c * 8);
+        *reinterpret_cast<uint4*>(sm + mat * 64 * PM_ROW + t * PM_ROW + c * 16) = v;
+        if (kc != nullptr && mat > 0 && t < T)
+            *reinterpret_cast<uint4*>((mat == 1 ? kc : vc) + (((int64_t)g * nh + h) * Tmax + t) * 64 + c * 8) = v;
+    }
+    __syncthreads();
+    if (16 * w >= T) return;                              // (no query rows for this warp)
+    const uint32_t qs = tc::smem_u32(Qs), ks = tc::smem_u32(Ks), vs = tc::smem_u32(Vs);
+    // ---- S = Q K^T for this warp's 16 query rows
+    float sacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        uint32_t a[4];
+        pa_ldsm4(a, qs + (uint32_t)((16 * w + (lane & 15)) * PM_ROW + kk * 32 + (lane >> 4) * 16));
+#pragma unroll
+        for (int jp = 0; jp < 4; jp++) {                 // two key tiles per ldmatrix.x4
+            uint32_t b[4];
+            pa_ldsm4(b, ks + (uint32_t)((16 * jp + (lane & 7) + ((lane >> 4) << 3)) * PM_ROW + kk * 32 + ((lane >> 3) & 1) * 16));
+            pa_mma<BF>(sacc[2 * jp], a, b[0], b[1]);
+            pa_mma<BF>(sacc[2 * jp + 1], a, b[2], b[3]);
+        }
+    }
+    // ---- scale, causal mask, softmax over the row (a row's 64 scores live in the 4 lanes of a quad: 16 each)
+    const int r0 = 16 * w + (lane >> 2), r1 = r0 + 8;
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c0 = 8 * j + (lane & 3) * 2;
+        sacc[j][0] = (c0 <= r0) ? sacc[j][0] * 0.125f : -INFINITY;
+        sacc[j][1] = (c0 + 1 <= r0) ? sacc[j][1] * 0.125f : -INFINITY;
+        sacc[j][2] = (c0 <= r1) ? sacc[j][2] * 0.125f : -INFINITY;
+        sacc[j][3] = (c0 + 1 <= r1) ? sacc[j][3] * 0.125f : -INFINITY;
+        m0 = fmaxf(m0, fmaxf(sacc[j][0], sacc[j][1]));
+        m1 = fmaxf(m1, fmaxf(sacc[j][2], sacc[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+    uint32_t pa[4][4];                                    // probabilities as A fragments, one per 16-key step
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float e0 = __expf(sacc[j][0] - m0), e1 = __expf(sacc[j][1] - m0), e2 = __expf(sacc[j][2] - m1), e3 = __expf(sacc[j][3] - m1);
+        s0 += e0 + e1;
+        s1 += e2 + e3;
+        pa[j >> 1][(j & 1) * 2] = pack_h16x2(e0, e1, BF ? 1 : 0);
+        pa[j >> 1][(j & 1) * 2 + 1] = pack_h16x2(e2, e3, BF ? 1 : 0);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    // ---- O = P V
+    float oacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {                      // 16 keys per step
+#pragma unroll
+        for (int jp = 0; jp < 4; jp++) {                 // two 8-dim output tiles per ldmatrix.x4.trans
+            uint32_t b[4];
+            pa_ldsm4_t(b, vs + (uint32_t)((16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * PM_ROW + (2 * jp + (lane >> 4)) * 16));
+            pa_mma<BF>(oacc[2 * jp], pa[kk], b[0], b[1]);
+            pa_mma<BF>(oacc[2 * jp + 1], pa[kk], b[2], b[3]);
+        }
+    }
+    const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int d = 8 * j + (lane & 3) * 2;
+        if (r0 < T) *reinterpret_cast<uint32_t*>(att + ((int64_t)r0 * G + g) * E + h * 64 + d) = pack_h16x2(oacc[j][0] * i0, oacc[j][1] * i0, BF ? 1 : 0);
+        if (r1 < T) *reinterpret_cast<uint32_t*>(att + ((int64_t)r1 * G + g) * E + h * 64 + d) = pack_h16x2(oacc[j][2] * i1, oacc[j][3] * i1, BF ? 1 : 0);
+    }
+}
+
 // token sources --------------------------------------------------------------------------------------------------
 // cond token s: x[b,:] = cond_emb[cond[b,s]] + pos_emb_cond[s]                      (transformers.py:224)
 // grid (B, n_tokens): token s = stt->s + blockIdx.y, written to row blockIdx.y * B + b
@@ -978,9 +1090,20 @@ static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blo
             p.bias = bw.bqkv; p.out = bb.QKV;
             RQB_TRY(launch_gemm_tc(maps[l].qkv, tx_xn, p, pdl, st));
         }
-        RQB_TRY(launch_pdl(prefill_attn_kernel, dim3((unsigned)(G * c.n_head)), dim3(128), prefill_attn_smem(T), st, pdl,
-                           (const h16*)bb.QKV, kc ? kc + kv_per_layer * l : nullptr, vc ? vc + kv_per_layer * l : nullptr, bb.ATT, G, T, E,
-                           c.n_head, Tmax, f.bf));
+        h16* kcl = kc ? kc + kv_per_layer * l : nullptr;
+        h16* vcl = vc ? vc + kv_per_layer * l : nullptr;
+        if (T >= 16 && T <= 64) {                         // one 64-key tile: the mma.sync form
+            if (f.bf) {
+                RQB_TRY(launch_pdl(prefill_attn_mma_kernel<true>, dim3((unsigned)(G * c.n_head)), dim3(128), (size_t)0, st, pdl,
+                                   (const h16*)bb.QKV, kcl, vcl, bb.ATT, G, T, E, c.n_head, Tmax));
+            } else {
+                RQB_TRY(launch_pdl(prefill_attn_mma_kernel<false>, dim3((unsigned)(G * c.n_head)), dim3(128), (size_t)0, st, pdl,
+                                   (const h16*)bb.QKV, kcl, vcl, bb.ATT, G, T, E, c.n_head, Tmax));
+            }
+        } else {
+            RQB_TRY(launch_pdl(prefill_attn_kernel, dim3((unsigned)(G * c.n_head)), dim3(128), prefill_attn_smem(T), st, pdl,
+                               (const h16*)bb.QKV, kcl, vcl, bb.ATT, G, T, E, c.n_head, Tmax, f.bf));
+        }
         if (rows) {
             RQB_TRY(launch_rows_gemm_tc(bb.ATT, bw.wproj, bw.bproj, bb.X, bb.X, nullptr, 0, f.bf, M, E, E, st));
         } else {

@@ -15,6 +15,8 @@
 // Persistent CTAs (grid = #SMs) loop over (pixel tile, cout tile) pairs; warp 0 = TMA producer, warp 1 = single-thread
 // tcgen05.mma issuer, warps 2-5 = epilogue.  Two TMEM accumulators (2 x BN columns) are ping-ponged so the epilogue of
 // tile i (TMEM -> registers -> +bias (+residual) -> fp32 NHWC / NCHW stores) overlaps the main loop of tile i+1.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -375,6 +377,10 @@ int launch_rows_gemm_tc(const void* X16, const void* W16, const float* bias, con
                         int gelu, int fmt, int64_t M, int N_out, int K, cudaStream_t st) {
     if (N_out % 128 != 0 || K % 64 != 0 || M < 1 || (out_f32 == nullptr) == (out_16 == nullptr) || bias == nullptr)
         return fail(RQB200_EINVAL, "rows_gemm_tc: need N_out % 128 == 0, K % 64 == 0, a bias and exactly one output");
+    // 256 x 256 tiles on CTA pairs when the shape allows (RQB200_ROWS_GEMM_1CTA=1, read once: this kernel for every shape)
+    static const bool one_cta = [] { const char* e = std::getenv("RQB200_ROWS_GEMM_1CTA"); return e && e[0] == '1'; }();
+    if (!one_cta && rows_gemm2_supported(M, N_out, K))
+        return launch_rows_gemm2_tc(X16, W16, bias, residual, out_f32, out_16, gelu, fmt, M, N_out, K, st);
     ConvTcParams p = {};
     p.B = (int)ceil_div(M, 128); p.H = 8; p.W = 16; p.Cin = K; p.Cout = N_out; p.ks = 1; p.stride = 1;
     p.TW = 16; p.TH = 8; p.NB = 1;

@@ -58,6 +58,10 @@ int launch_conv_tc(const void* X16, const void* W16, const void* X16lo, const vo
                    const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ks, int out_nchw,
                    cudaStream_t st, int stride = 1, double* gn_part = nullptr);
 bool conv_tc_gn_fusable(int H, int W, int Cout);
+// CTA-pair form (csrc/rows_gemm2.cu: cta_group::2, 256 x 256 tiles); launch_rows_gemm_tc dispatches to it when the shape allows
+bool rows_gemm2_supported(int64_t M, int N_out, int K);
+int launch_rows_gemm2_tc(const void* X16, const void* W16, const float* bias, const float* residual, float* out_f32, void* out_16,
+                         int gelu, int fmt, int64_t M, int N_out, int K, cudaStream_t st);
 int launch_rows_gemm_tc(const void* X16, const void* W16, const float* bias, const float* residual, float* out_f32, void* out_16,
                         int gelu, int fmt, int64_t M, int N_out, int K, cudaStream_t st);
 int launch_groupnorm_f16(const float* X, const float* gamma, const float* beta, void* Y16, void* Y16lo, double* stats_ws, int B,

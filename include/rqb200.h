@@ -48,6 +48,7 @@ extern "C" {
 #define RQB200_AR_BATCHED_DEEP_RING 64  /* large-M passes (prefill / forward) keep the deep ring: one CTA per SM                  */
 #define RQB200_AR_ATTN_ONE_WARP 256    /* body attention: one warp per (b, head) (round-1/2 form) instead of four               */
 #define RQB200_AR_TRACE_WEIGHTS 512    /* with TRACE: GEMM stamp 0 = prefetched weight tiles landed (instead of kernel entry)    */
+#define RQB200_AR_NO_PARAM_PREFETCH 1024 /* LN1 of block l does not prefetch block l+1's small vectors into L2                  */
 #define RQB200_AR_BATCHED_STREAMER 128  /* large-M passes through the weight-streaming GEMM instead of the persistent rows GEMM    */
 
 const char* rqb200_last_error(void);

@@ -63,17 +63,27 @@ static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
+// The per-block small vectors (biases, LayerNorm parameters: ~80 KB per block, read once per token) are DRAM misses -- 2.8 GB of
+// weights and the KV cache pass through L2 between two uses -- and each sits on a stage's critical path (a shared copy for all
+// blocks made the step 2 % faster, profiles/dropped_r2/shared_params_r2.txt).  LN1 of block l therefore asks L2 for block l+1's.
+struct PrefetchList {
+    const void* p[8];
+    uint32_t bytes[8];
+    int n;
+};
+
 // x_out = x_in + bias + sum_s partial[s] (+ extra row) ; xn = LayerNorm(x_out) in 16-bit.  One CTA per row.
 template <int THREADS, int NCH>
 __global__ void __launch_bounds__(THREADS)
 ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int S, const float* __restrict__ bias,
                  const float* __restrict__ extra, float* __restrict__ x_out, const float* __restrict__ g,
-                 const float* __restrict__ be, h16* __restrict__ xn, int B, int E, int bf, long long* tr) {
+                 const float* __restrict__ be, h16* __restrict__ xn, int B, int E, int bf, long long* tr, PrefetchList pf) {
     // each thread owns up to NCH float4 chunks of the row (E <= THREADS*4*NCH); every load is issued before the first dependent add and
     // the row stays in registers between the statistics and the normalisation
     __shared__ float red[33];
     tc::pdl_launch_dependents();
     TR_IN(tr);
+    if (blockIdx.x == 0 && threadIdx.x < pf.n) tc::bulk_prefetch_l2(pf.p[threadIdx.x], pf.bytes[threadIdx.x]);   // (parameters: no dependency)
     tc::pdl_wait();
     TR_DEP(tr);
     const int b = blockIdx.x;
@@ -736,7 +746,7 @@ struct ArFast {
     cudaGraphExec_t graphs[G_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     int64_t n_nodes[G_COUNT] = {0, 0, 0, 0};   // kernels recorded in each graph (for the launch counter)
     cudaStream_t cap_stream = nullptr;   // capture never happens on the caller's stream (it may be the legacy default stream)
-    bool use_graph = true, use_pdl = true, attn4 = true, deep = true, l2pf = false, batched_prefill = true, batched_deep = false, batched_streamer = false;
+    bool use_graph = true, use_pdl = true, attn4 = true, param_prefetch = true, deep = true, l2pf = false, batched_prefill = true, batched_deep = false, batched_streamer = false;
     int split_qkv = 4, split_proj = 12, split_fc1 = 1, split_fc2 = 12;
     int n_sm = 148;
     // diagnostic stage trace (cfg.flags & RQB200_AR_TRACE)
@@ -829,7 +839,8 @@ static int gemm(const ArFast& f, const char* name, const CUtensorMap& tw, const 
 }
 
 static int ln(const ArFast& f, const char* name, int rows, const float* x_in, const float* partial, int S, const float* bias,
-              const float* extra, float* x_out, const float* g, const float* be, h16* xn, cudaStream_t st) {
+              const float* extra, float* x_out, const float* g, const float* be, h16* xn, cudaStream_t st,
+              const PrefetchList* pf = nullptr) {
     const int E = f.cfg.embed_dim;
     if (rows >= 512 && S == 0 && bias == nullptr && x_in != nullptr) {        // batched passes: warp per row
         const dim3 grid((unsigned)std::min<int64_t>(ceil_div(rows, 8), (int64_t)f.n_sm * 8));
@@ -841,8 +852,9 @@ static int ln(const ArFast& f, const char* name, int rows, const float* x_in, co
         return RQB_LN_ROWS(36);
 #undef RQB_LN_ROWS
     }
+    PrefetchList none = {};
     return launch_pdl(ln_reduce_kernel<384, 3>, dim3((unsigned)rows), dim3(384), (size_t)0, st, f.use_pdl, x_in, partial, S, bias, extra, x_out,
-                      g, be, xn, rows, E, f.bf, tr_slot(f, name));
+                      g, be, xn, rows, E, f.bf, tr_slot(f, name), (pf && f.param_prefetch) ? *pf : none);
 }
 
 static int attn(const ArFast& f, FastWs& ws, const float* bqkv, h16* kc, h16* vc, int Tmax, const int* t_ptr, int t_host,
@@ -886,8 +898,17 @@ static int fast_stack(const ArFast& f, const std::vector<rqb200_block_weights>& 
         const bool first = l == 0;
         // LN1 (+ pending fc2 reduction of the previous block)
         const bool pend = l > 0;
+        PrefetchList pf = {};
+        if (l + 1 < blocks.size()) {
+            const rqb200_block_weights& nx = blocks[l + 1];
+            const void* ptrs[8] = {nx.ln1_w, nx.ln1_b, nx.bqkv, nx.bproj, nx.ln2_w, nx.ln2_b, nx.b1, bw.b2};
+            const uint32_t words[8] = {(uint32_t)E, (uint32_t)E, (uint32_t)(3 * E), (uint32_t)E, (uint32_t)E, (uint32_t)E, (uint32_t)(4 * E),
+                                       (uint32_t)E};
+            for (int i = 0; i < 8; i++) { pf.p[i] = ptrs[i]; pf.bytes[i] = words[i] * 4u; }
+            pf.n = 8;
+        }
         RQB_TRY(ln(f, "ln1", B, first ? x_src : x, pend ? ws.P : nof, pend ? f.split_fc2 : 0, pend ? blocks[l - 1].b2 : nof,
-                   first ? pending_extra : nof, x, bw.ln1_w, bw.ln1_b, ws.XN, st));
+                   first ? pending_extra : nof, x, bw.ln1_w, bw.ln1_b, ws.XN, st, &pf));
         RQB_TRY(gemm(f, "qkv", maps[l].qkv, f.tx_xn, 3 * E, E, B, f.split_qkv, GT_PARTIAL, nullptr, 1.f, nullptr, ws.P, nullptr, 0, nullptr, 0,
                      st));
         RQB_TRY(attn(f, ws, bw.bqkv, kc + per * l, vc + per * l, Tmax, t_ptr, t_host, st));
@@ -1010,6 +1031,7 @@ ArFast* ar_fast_create(const rqb200_ar_config& cfg, const rqb200_ar_weights& w, 
     f->l2pf = (cfg.flags & RQB200_AR_L2_PREFETCH) != 0;
     f->deep = !(cfg.flags & RQB200_AR_SHALLOW_RING);
     f->attn4 = !(cfg.flags & RQB200_AR_ATTN_ONE_WARP);
+    f->param_prefetch = !(cfg.flags & RQB200_AR_NO_PARAM_PREFETCH);
     f->batched_prefill = !(cfg.flags & RQB200_AR_SEQUENTIAL_PREFILL);
     f->batched_deep = (cfg.flags & RQB200_AR_BATCHED_DEEP_RING) != 0;
     f->batched_streamer = (cfg.flags & RQB200_AR_BATCHED_STREAMER) != 0;

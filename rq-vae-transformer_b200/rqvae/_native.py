@@ -11,7 +11,7 @@ OK, EINVAL, ECUDA, ENODEV, EWORKSPACE, ESTATE = 0, -1, -2, -3, -4, -5
 F32, BF16, F16 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
 AR_NO_GRAPH, AR_NO_PDL, AR_TRACE, AR_L2_PREFETCH, AR_SHALLOW_RING, AR_SEQUENTIAL_PREFILL, AR_BATCHED_DEEP_RING, AR_BATCHED_STREAMER = 1, 2, 4, 8, 16, 32, 64, 128
-AR_ATTN_ONE_WARP, AR_TRACE_WEIGHTS = 256, 512
+AR_ATTN_ONE_WARP, AR_TRACE_WEIGHTS, AR_NO_PARAM_PREFETCH = 256, 512, 1024
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 c_f32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p
@@ -178,6 +178,7 @@ def ar_engine_options():
     flags |= AR_BATCHED_DEEP_RING if env("RQB200_BATCHED_DEEP", "0") == "1" else 0
     flags |= AR_BATCHED_STREAMER if env("RQB200_BATCHED_STREAMER", "0") == "1" else 0
     flags |= AR_ATTN_ONE_WARP if env("RQB200_ATTN_ONE_WARP", "0") == "1" else 0
+    flags |= AR_NO_PARAM_PREFETCH if env("RQB200_NO_PARAM_PREFETCH", "0") == "1" else 0
     return {"flags": flags,
             "splits": [int(env("RQB200_SPLIT_" + k, "0")) for k in ("QKV", "PROJ", "FC1", "FC2")]}
 

@@ -666,6 +666,57 @@ prefill_attn_mma_kernel(const h16* __restrict__ qkv, h16* __restrict__ kc, h16* 
     }
 }
 
+// ... and for groups of at most 8 tokens (the head stack of the teacher-forced forward: D tokens per (position, batch row), ~10^5
+// (group, head) pairs): one WARP per pair, everything in registers, lane <-> dims (2*lane, 2*lane+1), scores by warp reductions.
+template <int TMAXS>
+__global__ void __launch_bounds__(128)
+prefill_attn_small_kernel(const h16* __restrict__ qkv, h16* __restrict__ kc, h16* __restrict__ vc, h16* __restrict__ att, int G, int T, int E,
+                          int nh, int Tmax, int bf) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t pair = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (pair >= (int64_t)G * nh) return;
+    const int g = (int)(pair / nh), h = (int)(pair % nh);
+    float2 q[TMAXS], k[TMAXS], v[TMAXS];
+#pragma unroll
+    for (int t = 0; t < TMAXS; t++)
+        if (t < T) {
+            const h16* row = qkv + ((int64_t)t * G + g) * 3 * E + h * 64 + 2 * lane;
+            const uint32_t q2 = *reinterpret_cast<const uint32_t*>(row), k2 = *reinterpret_cast<const uint32_t*>(row + E),
+                           v2 = *reinterpret_cast<const uint32_t*>(row + 2 * E);
+            q[t] = unpack_h16x2(q2, bf); k[t] = unpack_h16x2(k2, bf); v[t] = unpack_h16x2(v2, bf);
+            if (kc) {
+                *reinterpret_cast<uint32_t*>(kc + (((int64_t)g * nh + h) * Tmax + t) * 64 + 2 * lane) = k2;
+                *reinterpret_cast<uint32_t*>(vc + (((int64_t)g * nh + h) * Tmax + t) * 64 + 2 * lane) = v2;
+            }
+        }
+#pragma unroll
+    for (int t = 0; t < TMAXS; t++)
+        if (t < T) {
+            float sc[TMAXS];
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < TMAXS; j++)
+                if (j <= t) {
+                    sc[j] = warp_sum(fmaf(q[t].y, k[j].y, q[t].x * k[j].x)) * 0.125f;
+                    m = fmaxf(m, sc[j]);
+                }
+            float sum = 0.f;
+            float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < TMAXS; j++)
+                if (j <= t) {
+                    const float e = __expf(sc[j] - m);
+                    sum += e;
+                    o.x = fmaf(e, v[j].x, o.x);
+                    o.y = fmaf(e, v[j].y, o.y);
+                }
+            const float inv = 1.0f / sum;
+            *reinterpret_cast<uint32_t*>(att + ((int64_t)t * G + g) * E + h * 64 + 2 * lane) = pack_h16x2(o.x * inv, o.y * inv, bf);
+        }
+}
+
 // token sources --------------------------------------------------------------------------------------------------
 // cond token s: x[b,:] = cond_emb[cond[b,s]] + pos_emb_cond[s]                      (transformers.py:224)
 // grid (B, n_tokens): token s = stt->s + blockIdx.y, written to row blockIdx.y * B + b
@@ -1114,7 +1165,13 @@ static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blo
         }
         h16* kcl = kc ? kc + kv_per_layer * l : nullptr;
         h16* vcl = vc ? vc + kv_per_layer * l : nullptr;
-        if (T >= 16 && T <= 64) {                         // one 64-key tile: the mma.sync form
+        if (T <= 4) {                                     // tiny groups (the forward's head stack): a warp per (group, head)
+            RQB_TRY(launch_pdl(prefill_attn_small_kernel<4>, dim3((unsigned)ceil_div((int64_t)G * c.n_head, 4)), dim3(128), (size_t)0, st, pdl,
+                               (const h16*)bb.QKV, kcl, vcl, bb.ATT, G, T, E, c.n_head, Tmax, f.bf));
+        } else if (T <= 8) {
+            RQB_TRY(launch_pdl(prefill_attn_small_kernel<8>, dim3((unsigned)ceil_div((int64_t)G * c.n_head, 4)), dim3(128), (size_t)0, st, pdl,
+                               (const h16*)bb.QKV, kcl, vcl, bb.ATT, G, T, E, c.n_head, Tmax, f.bf));
+        } else if (T >= 16 && T <= 64) {                  // one 64-key tile: the mma.sync form
             if (f.bf) {
                 RQB_TRY(launch_pdl(prefill_attn_mma_kernel<true>, dim3((unsigned)(G * c.n_head)), dim3(128), (size_t)0, st, pdl,
                                    (const h16*)bb.QKV, kcl, vcl, bb.ATT, G, T, E, c.n_head, Tmax));

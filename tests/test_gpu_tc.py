@@ -126,7 +126,7 @@ def test_conv_tc_stride2_downsample(B, Ho, Cin, Cout, split):
     torch.testing.assert_close(out.permute(0, 3, 1, 2), ref, rtol=1e-4 if split else 2e-3, atol=1e-4 if split else 2e-3)
 
 
-@pytest.mark.parametrize("M,N_out,K", [(257, 1536, 1536), (2048, 4608, 1536), (1000, 1280, 5120), (4096, 256, 256), (130, 128, 64),
+@pytest.mark.parametrize("M,N_out,K", [(257, 1536, 1536), (2048, 4608, 1536), (1000, 1280, 5120), (4096, 256, 256), (130, 128, 64), (700, 512, 512),
                                        (6080, 6144, 1536)])
 @pytest.mark.parametrize("fmt", ["fp16", "bf16"])
 def test_rows_gemm_persistent_kernel(M, N_out, K, fmt):

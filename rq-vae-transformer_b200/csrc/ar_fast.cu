@@ -150,6 +150,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x_in, const float* __restrict__ extra, float* __restrict__ x_out, const float* __restrict__ g,
                const float* __restrict__ be, h16* __restrict__ xn, int64_t M, int E, int bf) {
+    tc::pdl_launch_dependents();
+    tc::pdl_wait();
     const int lane = threadIdx.x & 31;
     const int E4 = E >> 2;
     for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * 8) {
@@ -896,7 +898,7 @@ static int ln(const ArFast& f, const char* name, int rows, const float* x_in, co
     if (rows >= 512 && S == 0 && bias == nullptr && x_in != nullptr) {        // batched passes: warp per row
         const dim3 grid((unsigned)std::min<int64_t>(ceil_div(rows, 8), (int64_t)f.n_sm * 8));
         const int nv = ceil_div(E, 128);
-#define RQB_LN_ROWS(NV) launch_pdl(ln_rows_kernel<NV>, grid, dim3(256), (size_t)0, st, false, x_in, extra, x_out, g, be, xn, (int64_t)rows, E, f.bf)
+#define RQB_LN_ROWS(NV) launch_pdl(ln_rows_kernel<NV>, grid, dim3(256), (size_t)0, st, true, x_in, extra, x_out, g, be, xn, (int64_t)rows, E, f.bf)
         if (nv <= 8) return RQB_LN_ROWS(8);
         if (nv <= 12) return RQB_LN_ROWS(12);
         if (nv <= 20) return RQB_LN_ROWS(20);
@@ -1138,7 +1140,7 @@ static int stack_batched(ArFast& f, const std::vector<rqb200_block_weights>& blo
     const int E = c.embed_dim;
     const int64_t M = (int64_t)G * T;
     if (M > (int64_t)1 << 30 || T > PA_MAXT) return fail(RQB200_EINVAL, "ar fast tier: batched pass too large");
-    const bool pdl = false;              // large launches: plain stream order
+    const bool pdl = true;               // the pass is a PDL chain too: a launch's set-up overlaps its predecessor's tail
     CUtensorMap tx_xn, tx_att, tx_h;
     const int bn = gemm_tc_bn((int)std::min<int64_t>(M, 256));
     RQB_TRY(make_tmap_2d(&tx_xn, bb.XN, 1, E, M, (uint64_t)E * 2, 64, bn));

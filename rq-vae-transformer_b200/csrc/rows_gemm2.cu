@@ -107,6 +107,7 @@ rows_gemm2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint64_t* tempty = tfull + 2;            // [2]  (the leader's copy is the one that counts)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+    tc::pdl_launch_dependents();            // the next launch of the pass may set itself up while this one runs
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = g2::cluster_ctarank();
     const bool leader = rank == 0;
@@ -126,6 +127,7 @@ rows_gemm2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     g2::cluster_sync();                      // barriers initialised and TMEM allocated in both CTAs before anyone signals the peer
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc::pdl_wait();                          // barriers, TMEM and the cluster hand-shake are done ahead of the upstream kernel's end
 
     if (warp == 0) {
         if (lane == 0) {
@@ -272,8 +274,17 @@ int launch_rows_gemm2_tc(const void* X16, const void* W16, const float* bias, co
     RQB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     const int total = p.m_tiles * p.n_tiles;
     const int pairs = std::max(1, std::min(total, n_sm / 2));
-    rows_gemm2_kernel<<<2 * pairs, G2_THREADS, smem, st>>>(tmX, tmW, p);
-    RQB_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(G2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RQB_CUDA(cudaLaunchKernelEx(&cfg, rows_gemm2_kernel, tmX, tmW, p));
     g_launches++;
     return 0;
 }

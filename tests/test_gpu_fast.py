@@ -266,3 +266,25 @@ def test_fast_tier_batched_forward(golden, layouts, name):
         e = float((cond_logits.cpu() - cref).abs().max())
         print("%s: cond_logits vs oracle: max error %.2e (std %.3f)" % (name, e, float(cref.std())))
         assert e < 0.04 * float(cref.std())
+
+
+@pytest.mark.parametrize("name", ["tiny", "in1400m"])
+def test_fast_tier_batched_forward_bf16(golden, layouts, name):
+    """the batched passes in the bf16 operand format (the bf16 instantiations of the mma.sync attention / pair GEMM / LayerNorm
+    kernels): batched forward == the same tier's sequential teacher-forced replay up to summation order"""
+    g, model, aux, cond, bs, V = _case(name, golden, layouts)
+    codes = g["runs"][-1]["codes"].long().to(DEV)
+    B = codes.shape[0]
+    model.precision = "fast"
+
+    def run():
+        out = model(codes, model_aux=aux, cond=cond, amp=True)
+        out = out[0] if isinstance(out, tuple) else out
+        _, seq = model._native_sample(codes, aux, cond, (0, 0), 1.0, None, None, True, noise=False, return_logits=True, force_codes=codes)
+        return out, seq.reshape(*bs, B, V).permute(3, 0, 1, 2, 4)
+
+    out, seq = _with_env(model, {"RQB200_FAST_DTYPE": "bf16"}, run)
+    std = float(seq.std())
+    d = float((out - seq).abs().max())
+    print("%s: bf16 batched forward vs sequential replay: max logit difference %.2e (std %.3f)" % (name, d, std))
+    assert d < 0.15 * std           # (bf16: 8-bit mantissa; the fp16 gate is 0.02)

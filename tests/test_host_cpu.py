@@ -118,6 +118,18 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert N.lib().rqb200_version() >= 100
 
 
+def test_engine_flag_constants_match_the_header():
+    """the binding's AR_* flag values are the header's RQB200_AR_* defines (one bit each, no overlap)"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "rqb200.h")).read()
+    flags = {n: int(v) for n, v in re.findall(r"#define\s+RQB200_(AR_[A-Z0-9_]+)\s+(\d+)", hdr)}
+    assert len(flags) >= 8
+    for name, value in flags.items():
+        assert value & (value - 1) == 0, name
+        assert getattr(N, name) == value, name
+    assert len(set(flags.values())) == len(flags)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
 def test_no_cpu_fallback():
     """the product path must fail loudly, never compute on the CPU"""

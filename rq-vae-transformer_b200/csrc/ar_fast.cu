@@ -73,6 +73,8 @@ struct PrefetchList {
 };
 
 // x_out = x_in + bias + sum_s partial[s] (+ extra row) ; xn = LayerNorm(x_out) in 16-bit.  One CTA per row.
+// (instantiated as <384, 3> only: 192-thread CTAs with two chunks per thread, padded grids and a 2-CTA-cluster form all measured
+//  equal or slower, profiles/dropped_r2/ln_grid_threads_r2.txt)
 template <int THREADS, int NCH>
 __global__ void __launch_bounds__(THREADS)
 ln_reduce_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int S, const float* __restrict__ bias,

@@ -1,4 +1,5 @@
-"""Pipelining experiment: decode of batch i on a second stream (persistent conv kernels confined to `dec_sms` SMs) while batch i+1 is
+"""(NOT RUNNABLE ANY MORE: needs the removed rqb200_set_conv_sm_limit entry point and the high-priority graph capture; kept as the record of
+what overlap_r2.txt measured.)  Pipelining experiment: decode of batch i on a second stream (persistent conv kernels confined to `dec_sms` SMs) while batch i+1 is
 sampled on the first stream (GEMM grids shrunk to what is left).   usage: python profiles/exp_overlap.py [dec_sms ...]"""
 import os
 import sys

@@ -6,9 +6,10 @@
 // tcgen05.mma.cta_group::2, one 256 x 256 x 16 instruction per K step for two SMs: CTA r of the pair stages rows [128 r, 128 r + 128)
 // of the 256-row X tile and rows [128 r, +128) of the 256-row W tile (its half of the N extent), the leader CTA's single thread
 // issues the MMAs for both, and each CTA's TMEM receives the accumulator rows of its own 128 X rows.  Per 64-wide K block an SM
-// therefore pulls 32 KB through TMA for 512 tensor-pipe cycles; the single-CTA 128 x 256 tile of conv_tc_kernel needs 48 KB for
-// the same 512 cycles, which is above what one SM's TMA path delivers (67-75 B/clk, profiles/bench_tma_r2.txt): that kernel is
-// fill-bound at ~3/4 of the tensor rate, this one is not.
+// therefore pulls 32 KB out of L2 for 512 tensor-pipe cycles (62.5 B/clk at full rate); the single-CTA 128 x 256 tile of
+// conv_tc_kernel needs 48 KB for the same 512 cycles (94 B/clk).  What limits both is the L2 -> SM fabric with all 148 SMs loading:
+// ncu reads 453 MB of l1tex__m_xbar2l1tex_read_bytes for the 52 us qkv launch of this kernel = 8.7 TB/s = ~45 B/clk per SM, at 66 %
+// tensor-pipe activity -- the pair form needs a third fewer bytes per flop and is that much closer to the tensor rate.
 //
 // Persistent: one CTA pair per two SMs, tiles strided over the pairs; a 6-deep TMA ring; TWO accumulators (2 x 256 TMEM columns,
 // the whole 512-column TMEM) so that the eight epilogue warps of each CTA drain tile i while the MMAs of tile i+1 run.
